@@ -1,0 +1,8 @@
+"""approx_counter_b200 — B200 (sm_100a) implementation of approx_counter's
+approximate k-mer counting path.  CUDA kernels and the C ABI live in csrc/
+(libapc.so); this package is the ctypes binding used by tests and bench.py.
+"""
+from ._lib import ApcError, LIB_PATH, load  # noqa: F401
+from .api import ApproxCounter, device_count  # noqa: F401
+
+__all__ = ["ApproxCounter", "ApcError", "device_count", "load", "LIB_PATH"]

@@ -1,0 +1,165 @@
+"""Host-side mirror of the reference's interface for the counting path, bound to
+libapc's C ABI (include/apc.h).  Names follow /root/reference/approx_counter.cpp:
+`errorCount` (:531), `count_kmers` (:487) + `get_most_frequent` (:396).
+
+Nothing here computes on the CPU: every method is a thin ctypes call into the
+CUDA library, and raises ApcError / ImportError when that is impossible.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ApcError, ApcTiming
+
+
+def _as_kmers(kmers):
+    return np.ascontiguousarray(kmers, dtype=np.uint64)
+
+
+class ApproxCounter:
+    """One GPU's worth of the path: upload the sampled read ends once, then run
+    the exact top-N and the approximate count against them."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        st = self._lib.apc_create(int(device), C.byref(h))
+        if st != _lib.APC_OK:
+            raise ApcError(st, self._lib.apc_strerror(st).decode())
+        self._h = h
+        self.device = int(device)
+        if stream is not None:
+            self.set_stream(stream)
+
+    # -- plumbing ---------------------------------------------------------------
+    def _check(self, st):
+        if st != _lib.APC_OK:
+            raise ApcError(st, self._lib.apc_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.apc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.Stream().cuda_stream) or None."""
+        self._check(self._lib.apc_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+
+    def sync(self):
+        self._check(self._lib.apc_sync(self._h))
+
+    def set_option(self, name, value):
+        self._check(self._lib.apc_set_option(self._h, name.encode(), int(value)))
+
+    # -- sample -------------------------------------------------------------------
+    def upload_sample(self, sample):
+        """sample: uint8[n, L] ASCII matrix (uniform length), or a list of
+        str/bytes (ragged).  Mirrors handing `sample` to errorCount (:922)."""
+        if isinstance(sample, np.ndarray):
+            if sample.ndim != 2 or sample.dtype != np.uint8:
+                raise ValueError("sample matrix must be uint8[n, L]")
+            m = np.ascontiguousarray(sample)
+            self._check(self._lib.apc_upload_sample(self._h, m.ctypes.data, m.shape[0], m.shape[1]))
+            return
+        bs = [r.encode() if isinstance(r, str) else bytes(r) for r in sample]
+        offs = np.zeros(len(bs) + 1, np.uint64)
+        if bs:
+            offs[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+        raw = np.frombuffer(b"".join(bs) or b"\0", np.uint8)
+        self._check(self._lib.apc_upload_sample_ragged(self._h, raw.ctypes.data, offs.ctypes.data, len(bs)))
+
+    def upload_sample_ptr(self, host_ptr, n_reads, read_len):
+        """Same, from a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
+        self._check(self._lib.apc_upload_sample(self._h, C.c_void_p(int(host_ptr)), int(n_reads), int(read_len)))
+
+    def sample_info(self):
+        n, ml, tb = C.c_uint64(), C.c_uint32(), C.c_uint64()
+        self._check(self._lib.apc_sample_info(self._h, C.byref(n), C.byref(ml), C.byref(tb)))
+        return n.value, ml.value, tb.value
+
+    # -- exact stage (:487-519 + :396-405) ------------------------------------------
+    def count_kmers_topn(self, k, lc_adjusted, lim, forbidden=None):
+        """-> (kmers u64[n], counts u64[n], n_distinct, had_n), CompareCount order."""
+        fb = None if forbidden is None else _as_kmers(forbidden)
+        km = np.zeros(max(1, lim), np.uint64)
+        ct = np.zeros(max(1, lim), np.uint64)
+        n, nd, hn = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.apc_exact_topn(
+            self._h, int(k), float(lc_adjusted), int(lim),
+            None if fb is None else fb.ctypes.data, 0 if fb is None else len(fb),
+            km.ctypes.data, ct.ctypes.data, C.byref(n), C.byref(nd), C.byref(hn)))
+        return km[: n.value].copy(), ct[: n.value].copy(), nd.value, hn.value
+
+    def solid_kmers(self, k, lc_adjusted, solid_km, forbidden=None, capacity=1 << 20):
+        fb = None if forbidden is None else _as_kmers(forbidden)
+        while True:
+            km = np.zeros(max(1, capacity), np.uint64)
+            ct = np.zeros(max(1, capacity), np.uint64)
+            n, nd, hn = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            st = self._lib.apc_exact_solid(
+                self._h, int(k), float(lc_adjusted), int(solid_km),
+                None if fb is None else fb.ctypes.data, 0 if fb is None else len(fb),
+                km.ctypes.data, ct.ctypes.data, capacity, C.byref(n), C.byref(nd), C.byref(hn))
+            if st == -7:  # APC_ERR_CAPACITY
+                capacity = int(n.value)
+                continue
+            self._check(st)
+            return km[: n.value].copy(), ct[: n.value].copy(), nd.value, hn.value
+
+    # -- approximate stage (:531-601) ---------------------------------------------------
+    def errorCount(self, kmers, k):
+        """counts[i] = sum_e |reads flagged at error level e| for kmers[i] (host in/out)."""
+        km = _as_kmers(kmers)
+        out = np.zeros(len(km), np.uint64)
+        self._check(self._lib.apc_approx_count(self._h, int(k), km.ctypes.data, len(km), out.ctypes.data))
+        return out
+
+    def errorCount_ptr(self, kmers_ptr, n_kmers, k, counts_ptr):
+        self._check(self._lib.apc_approx_count(self._h, int(k), C.c_void_p(int(kmers_ptr)), int(n_kmers),
+                                               C.c_void_p(int(counts_ptr))))
+
+    def set_queries(self, kmers, k):
+        km = _as_kmers(kmers)
+        self._n_kmers = len(km)
+        self._check(self._lib.apc_set_queries(self._h, int(k), km.ctypes.data, len(km)))
+
+    def scan(self, d_counts_ptr=None):
+        """Launch the scan on the context's stream (asynchronous)."""
+        self._check(self._lib.apc_scan(self._h, C.c_void_p(int(d_counts_ptr) if d_counts_ptr else 0)))
+
+    def get_counts(self):
+        out = np.zeros(self._n_kmers, np.uint64)
+        self._check(self._lib.apc_get_counts(self._h, out.ctypes.data))
+        return out
+
+    def counts_device_ptr(self):
+        return int(self._lib.apc_counts_device_ptr(self._h) or 0)
+
+    def timing(self):
+        t = ApcTiming()
+        self._check(self._lib.apc_last_timing(self._h, C.byref(t)))
+        return {"upload_ms": t.upload_ms, "exact_ms": t.exact_ms, "scan_ms": t.scan_ms,
+                "total_ms": t.total_ms, "scan_launches": int(t.scan_launches)}
+
+    def measure_int_peak(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        self._check(self._lib.apc_measure_int_peak(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"lop3_ops_per_s": a.value, "imad_ops_per_s": b.value, "mixed_ops_per_s": c.value}
+
+
+def device_count():
+    n = _lib.load().apc_device_count()
+    return max(0, n)

@@ -1,0 +1,346 @@
+// apc_api.cu — the C ABI of libapc (include/apc.h): context, sample upload,
+// query upload, scan, result read-back, timing.  Plain pointers and sizes
+// only; every CUDA failure becomes a status code plus apc_last_error text.
+#include <cstring>
+#include <new>
+
+#include "apc_internal.h"
+
+namespace apc {
+
+int fail(Ctx *c, int status, const char *what, cudaError_t e) {
+    if (c) {
+        c->err = what ? what : "";
+        if (e != cudaSuccess) {
+            c->err += ": ";
+            c->err += cudaGetErrorString(e);
+        }
+    }
+    return status;
+}
+
+static int bind(Ctx *c) {
+    if (!c) return APC_ERR_INVALID;
+    APC_CUDA(c, cudaSetDevice(c->device));
+    return APC_OK;
+}
+
+template <typename T>
+static int grow(Ctx *c, T *&ptr, size_t &cap, size_t need_bytes) {
+    if (need_bytes <= cap && ptr) return APC_OK;
+    if (ptr) {
+        APC_CUDA(c, cudaStreamSynchronize(c->stream));
+        APC_CUDA(c, cudaFree(ptr));
+        ptr = nullptr;
+        cap = 0;
+    }
+    if (need_bytes == 0) need_bytes = 16;
+    cudaError_t e = cudaMalloc((void **)&ptr, need_bytes);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        return fail(c, e == cudaErrorMemoryAllocation ? APC_ERR_NOMEM : APC_ERR_CUDA, "cudaMalloc", e);
+    }
+    cap = need_bytes;
+    return APC_OK;
+}
+
+static float elapsed(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(b) != cudaSuccess) return 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) return 0.f;
+    return ms;
+}
+
+static int prepare_sample(Ctx *c, uint64_t n_reads, uint32_t max_len, uint64_t total_bases) {
+    if (n_reads > 0xFFFFFFFFull * kTileReads) return fail(c, APC_ERR_INVALID, "too many reads");
+    c->n_reads = n_reads;
+    c->max_len = max_len;
+    c->total_bases = total_bases;
+    c->n_tiles = (uint32_t)((n_reads + kTileReads - 1) / kTileReads);
+    c->chunks = (max_len + kChunkBases - 1) / kChunkBases;
+    const size_t tiles_bytes = (size_t)c->n_tiles * c->chunks * kTileReads * sizeof(uint4);
+    int st = grow(c, c->d_tiles, c->tiles_bytes, tiles_bytes);
+    if (st) return st;
+    const size_t lens_bytes = ((size_t)c->n_tiles * kTileReads + 1) * sizeof(uint32_t);
+    if ((st = grow(c, c->d_lens, c->lens_cap, lens_bytes))) return st;
+    APC_CUDA(c, cudaMemsetAsync(c->d_lens, 0, lens_bytes, c->stream));
+    c->has_sample = true;
+    return APC_OK;
+}
+
+} // namespace apc
+
+using apc::Ctx;
+
+extern "C" {
+
+int apc_version(void) { return APC_VERSION; }
+
+const char *apc_strerror(int status) {
+    switch (status) {
+    case APC_OK: return "ok";
+    case APC_ERR_INVALID: return "invalid argument";
+    case APC_ERR_CUDA: return "CUDA runtime error";
+    case APC_ERR_NO_DEVICE: return "no usable CUDA device";
+    case APC_ERR_NO_SAMPLE: return "no sample uploaded";
+    case APC_ERR_NO_QUERIES: return "no queries set";
+    case APC_ERR_NOMEM: return "out of memory";
+    case APC_ERR_CAPACITY: return "output capacity too small";
+    default: return "unknown status";
+    }
+}
+
+int apc_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return APC_ERR_NO_DEVICE;
+    }
+    return n;
+}
+
+int apc_create(int device, apc_ctx **out) {
+    if (!out) return APC_ERR_INVALID;
+    *out = nullptr;
+    int n = apc_device_count();
+    if (n <= 0 || device < 0 || device >= n) return APC_ERR_NO_DEVICE;
+    apc_ctx *c = new (std::nothrow) apc_ctx();
+    if (!c) return APC_ERR_NOMEM;
+    c->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) {
+        apc_destroy(c);
+        return APC_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return APC_OK;
+}
+
+void apc_destroy(apc_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_tiles);
+    cudaFree(c->d_lens);
+    cudaFree(c->d_peq);
+    cudaFree(c->d_counts);
+    cudaFree(c->d_stage);
+    cudaFree(c->d_stage_offs);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (auto &e : c->ev)
+        if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char *apc_last_error(const apc_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int apc_set_stream(apc_ctx *c, void *cuda_stream) {
+    if (!c) return APC_ERR_INVALID;
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return APC_OK;
+}
+
+int apc_sync(apc_ctx *c) {
+    int st = apc::bind(c);
+    if (st) return st;
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return APC_OK;
+}
+
+int apc_upload_sample(apc_ctx *c, const uint8_t *bases, uint64_t n_reads, uint32_t read_len) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (!bases && n_reads * read_len) return apc::fail(c, APC_ERR_INVALID, "bases is NULL");
+    APC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    const size_t bytes = (size_t)n_reads * read_len;
+    if ((st = apc::prepare_sample(c, n_reads, read_len, bytes))) return st;
+    c->uniform_len = true;
+    if ((st = apc::grow(c, c->d_stage, c->stage_cap, bytes))) return st;
+    if (bytes) APC_CUDA(c, cudaMemcpyAsync(c->d_stage, bases, bytes, cudaMemcpyHostToDevice, c->stream));
+    APC_CUDA(c, apc::launch_build_tiles_uniform(c->d_stage, n_reads, read_len, c->chunks, c->n_tiles,
+                                                c->d_tiles, c->d_lens, c->stream));
+    APC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream)); // caller may free `bases` on return
+    c->timing.upload_ms = apc::elapsed(c->ev[0], c->ev[1]);
+    return APC_OK;
+}
+
+int apc_upload_sample_ragged(apc_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (!offsets && n_reads) return apc::fail(c, APC_ERR_INVALID, "offsets is NULL");
+    uint64_t total = n_reads ? offsets[n_reads] - offsets[0] : 0;
+    if (!bases && total) return apc::fail(c, APC_ERR_INVALID, "bases is NULL");
+    uint32_t max_len = 0;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        if (offsets[r + 1] < offsets[r]) return apc::fail(c, APC_ERR_INVALID, "offsets not monotone");
+        const uint64_t len = offsets[r + 1] - offsets[r];
+        if (len > 0xFFFFFFFFull) return apc::fail(c, APC_ERR_INVALID, "read too long");
+        if (len > max_len) max_len = (uint32_t)len;
+    }
+    APC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if ((st = apc::prepare_sample(c, n_reads, max_len, total))) return st;
+    c->uniform_len = false;
+    if ((st = apc::grow(c, c->d_stage, c->stage_cap, (size_t)total))) return st;
+    if ((st = apc::grow(c, c->d_stage_offs, c->stage_offs_cap, (size_t)(n_reads + 1) * sizeof(uint64_t)))) return st;
+    if (n_reads) {
+        const uint64_t base0 = offsets[0];
+        if (total) APC_CUDA(c, cudaMemcpyAsync(c->d_stage, bases + base0, total, cudaMemcpyHostToDevice, c->stream));
+        std::vector<uint64_t> rel(n_reads + 1);
+        for (uint64_t r = 0; r <= n_reads; r++) rel[r] = offsets[r] - base0;
+        APC_CUDA(c, cudaMemcpyAsync(c->d_stage_offs, rel.data(), (n_reads + 1) * sizeof(uint64_t),
+                                    cudaMemcpyHostToDevice, c->stream));
+        APC_CUDA(c, cudaStreamSynchronize(c->stream)); // rel goes out of scope
+    }
+    APC_CUDA(c, apc::launch_build_tiles_ragged(c->d_stage, c->d_stage_offs, n_reads, c->chunks, c->n_tiles,
+                                               c->d_tiles, c->d_lens, c->stream));
+    APC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->timing.upload_ms = apc::elapsed(c->ev[0], c->ev[1]);
+    return APC_OK;
+}
+
+int apc_sample_info(const apc_ctx *c, uint64_t *n_reads, uint32_t *max_len, uint64_t *total_bases) {
+    if (!c) return APC_ERR_INVALID;
+    if (n_reads) *n_reads = c->n_reads;
+    if (max_len) *max_len = c->max_len;
+    if (total_bases) *total_bases = c->total_bases;
+    return APC_OK;
+}
+
+static int exact_common(apc_ctx *c, uint8_t k, float lc, uint64_t lim, uint64_t solid_km,
+                        const uint64_t *forbidden, uint64_t n_forbidden, uint64_t *kmers_out,
+                        uint64_t *counts_out, uint64_t capacity, uint64_t *n_out, uint64_t *n_distinct,
+                        uint64_t *n_had_n) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (k < 2 || k > 32) return apc::fail(c, APC_ERR_INVALID, "k must be in [2,32]");
+    if (!c->has_sample) return apc::fail(c, APC_ERR_NO_SAMPLE, "exact stage: no sample uploaded");
+    if (!n_out || (!forbidden && n_forbidden)) return apc::fail(c, APC_ERR_INVALID, "NULL argument");
+    std::vector<uint64_t> km, ct;
+    if ((st = apc::exact_count_select(c, k, lc, lim, solid_km, forbidden, n_forbidden, km, ct, n_distinct, n_had_n)))
+        return st;
+    *n_out = km.size();
+    if (km.size() > capacity) return apc::fail(c, APC_ERR_CAPACITY, "output capacity too small");
+    if (!km.empty() && (!kmers_out || !counts_out)) return apc::fail(c, APC_ERR_INVALID, "NULL output");
+    for (size_t i = 0; i < km.size(); i++) { kmers_out[i] = km[i]; counts_out[i] = ct[i]; }
+    return APC_OK;
+}
+
+int apc_exact_topn(apc_ctx *c, uint8_t k, float lc_adjusted, uint64_t lim, const uint64_t *forbidden,
+                   uint64_t n_forbidden, uint64_t *kmers_out, uint64_t *counts_out, uint64_t *n_out,
+                   uint64_t *n_distinct, uint64_t *n_had_n) {
+    return exact_common(c, k, lc_adjusted, lim, 0, forbidden, n_forbidden, kmers_out, counts_out, lim, n_out,
+                        n_distinct, n_had_n);
+}
+
+int apc_exact_solid(apc_ctx *c, uint8_t k, float lc_adjusted, uint64_t solid_km, const uint64_t *forbidden,
+                    uint64_t n_forbidden, uint64_t *kmers_out, uint64_t *counts_out, uint64_t capacity,
+                    uint64_t *n_out, uint64_t *n_distinct, uint64_t *n_had_n) {
+    if (solid_km == 0) return apc::fail(c, APC_ERR_INVALID, "solid_km must be > 0");
+    return exact_common(c, k, lc_adjusted, ~0ull, solid_km, forbidden, n_forbidden, kmers_out, counts_out,
+                        capacity, n_out, n_distinct, n_had_n);
+}
+
+int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kmers) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (k < 2 || k > 32) return apc::fail(c, APC_ERR_INVALID, "k must be in [2,32]");
+    if (!kmers && n_kmers) return apc::fail(c, APC_ERR_INVALID, "kmers is NULL");
+    if (k < 32)
+        for (uint32_t i = 0; i < n_kmers; i++)
+            if (kmers[i] >> (2 * k)) return apc::fail(c, APC_ERR_INVALID, "k-mer value wider than 2k bits");
+    c->k = k;
+    c->n_kmers = n_kmers;
+    c->variant = apc::pick_variant(k, c->opt_variant);
+    std::vector<uint32_t> table;
+    apc::build_peq_tables(kmers, n_kmers, k, c->variant, table, c->n_groups);
+    if ((st = apc::grow(c, c->d_peq, c->peq_cap, table.size() * sizeof(uint32_t)))) return st;
+    const size_t slots = (size_t)c->n_groups * c->variant.queries_per_group();
+    if ((st = apc::grow(c, c->d_counts, c->counts_cap, slots * sizeof(unsigned long long)))) return st;
+    if (!table.empty()) {
+        APC_CUDA(c, cudaMemcpyAsync(c->d_peq, table.data(), table.size() * sizeof(uint32_t),
+                                    cudaMemcpyHostToDevice, c->stream));
+        APC_CUDA(c, cudaStreamSynchronize(c->stream)); // table is a local
+    }
+    return APC_OK;
+}
+
+int apc_scan(apc_ctx *c, uint64_t *d_counts) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (!c->has_sample) return apc::fail(c, APC_ERR_NO_SAMPLE, "apc_scan: no sample uploaded");
+    if (c->k == 0) return apc::fail(c, APC_ERR_NO_QUERIES, "apc_scan: no queries");
+    unsigned long long *dst = d_counts ? (unsigned long long *)d_counts : c->d_counts;
+    APC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    APC_CUDA(c, apc::launch_scan(*c, dst, &c->timing.scan_launches));
+    APC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    c->timing.scan_ms = -1.f; // resolved lazily by apc_last_timing / apc_get_counts
+    return APC_OK;
+}
+
+int apc_get_counts(apc_ctx *c, uint64_t *counts_out) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (c->k == 0) return apc::fail(c, APC_ERR_NO_QUERIES, "apc_get_counts: no queries");
+    if (!counts_out && c->n_kmers) return apc::fail(c, APC_ERR_INVALID, "counts_out is NULL");
+    if (c->n_kmers)
+        APC_CUDA(c, cudaMemcpyAsync(counts_out, c->d_counts, (size_t)c->n_kmers * sizeof(uint64_t),
+                                    cudaMemcpyDeviceToHost, c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return APC_OK;
+}
+
+uint64_t *apc_counts_device_ptr(apc_ctx *c) { return c ? (uint64_t *)c->d_counts : nullptr; }
+
+int apc_approx_count(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kmers, uint64_t *counts_out) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (!c->has_sample) return apc::fail(c, APC_ERR_NO_SAMPLE, "apc_approx_count: no sample uploaded");
+    APC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if ((st = apc_set_queries(c, k, kmers, n_kmers))) return st;
+    if ((st = apc_scan(c, nullptr))) return st;
+    if ((st = apc_get_counts(c, counts_out))) return st;
+    APC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    c->timing.total_ms = apc::elapsed(c->ev[0], c->ev[1]);
+    return APC_OK;
+}
+
+int apc_last_timing(const apc_ctx *cc, apc_timing *out) {
+    apc_ctx *c = const_cast<apc_ctx *>(cc);
+    if (!c || !out) return APC_ERR_INVALID;
+    if (c->timing.scan_ms < 0.f) c->timing.scan_ms = apc::elapsed(c->ev[2], c->ev[3]);
+    *out = c->timing;
+    return APC_OK;
+}
+
+int apc_set_option(apc_ctx *c, const char *name, int64_t value) {
+    if (!c || !name) return APC_ERR_INVALID;
+    if (!std::strcmp(name, "scan_variant")) {
+        if (value != 0 && value != 1 && value != 2 && value != 3 && value != 6)
+            return apc::fail(c, APC_ERR_INVALID, "scan_variant must be 0,1,2,3 or 6");
+        c->opt_variant = (int)value;
+        return APC_OK;
+    }
+    if (!std::strcmp(name, "tiles_per_job")) {
+        if (value < 0 || value > (1 << 20)) return apc::fail(c, APC_ERR_INVALID, "tiles_per_job out of range");
+        c->opt_tiles_per_job = (int)value;
+        return APC_OK;
+    }
+    return apc::fail(c, APC_ERR_INVALID, "unknown option");
+}
+
+int apc_measure_int_peak(apc_ctx *c, double *lop3, double *imad, double *mixed) {
+    int st = apc::bind(c);
+    if (st) return st;
+    APC_CUDA(c, apc::measure_int_peak(*c, lop3, imad, mixed));
+    return APC_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,115 @@
+// apc_internal.h — context layout and launch declarations shared by libapc's
+// translation units.  Not part of the ABI (see include/apc.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "apc.h"
+
+namespace apc {
+
+// ---- scan-tile geometry -------------------------------------------------------
+// The sampled text lives in HBM as tiles of 32 reads (one read per lane).  A
+// tile is stored column-chunk-major: uint4 tile[chunks][32]; each uint4 holds
+// 16 consecutive bases of one read, one byte per base, already scaled to the
+// byte offset of that base's row in the 16-byte-per-row match table:
+//   A=0x00 C=0x10 G=0x20 T=0x30 N/pad=0x40.
+// A warp's 128-bit loads of one chunk are therefore one coalesced 512-byte
+// request, and a base costs one byte-extract before it becomes an LDS address.
+constexpr int kTileReads = 32;
+constexpr int kChunkBases = 16;
+constexpr uint32_t kCodeN = 0x40;
+constexpr int kPeqRows = 5;        // A C G T N
+constexpr int kWordsPerThread = 4; // u32 state words per thread = one 16-byte table row
+constexpr int kScanWarps = 8;      // warps per CTA of the scan kernel
+
+struct ScanVariant {
+    int nw; // u32 words per unit (1 or 2)
+    int f;  // k-mers interleaved per unit
+    int queries_per_group() const { return f * kWordsPerThread / nw; }
+};
+
+struct Ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+
+    // sample
+    uint4 *d_tiles = nullptr;
+    size_t tiles_bytes = 0;
+    uint32_t *d_lens = nullptr; // per-read length — exact stage
+    size_t lens_cap = 0;
+    bool has_sample = false;
+    uint64_t n_reads = 0;
+    uint32_t max_len = 0;
+    uint64_t total_bases = 0;
+    uint32_t n_tiles = 0;
+    uint32_t chunks = 0; // uint4 chunks per read
+    bool uniform_len = true;
+
+    // queries
+    uint8_t k = 0;
+    uint32_t n_kmers = 0;
+    ScanVariant variant{1, 1};
+    uint32_t n_groups = 0;
+    uint32_t *d_peq = nullptr; // [n_groups][5][4]
+    size_t peq_cap = 0;
+    unsigned long long *d_counts = nullptr; // [n_groups * queries_per_group]
+    size_t counts_cap = 0;
+
+    // staging
+    uint8_t *d_stage = nullptr;
+    size_t stage_cap = 0;
+    uint64_t *d_stage_offs = nullptr;
+    size_t stage_offs_cap = 0;
+    void *h_pinned = nullptr;
+    size_t pinned_cap = 0;
+
+    // options
+    int opt_variant = 0;
+    int opt_tiles_per_job = 0;
+
+    apc_timing timing{};
+};
+
+int fail(Ctx *c, int status, const char *what, cudaError_t e = cudaSuccess);
+
+#define APC_CUDA(ctx, call)                                                   \
+    do {                                                                      \
+        cudaError_t e__ = (call);                                             \
+        if (e__ != cudaSuccess) return ::apc::fail((ctx), APC_ERR_CUDA, #call, e__); \
+    } while (0)
+
+// sample_kernels.cu
+cudaError_t launch_build_tiles_uniform(const uint8_t *d_ascii, uint64_t n_reads, uint32_t read_len,
+                                       uint32_t chunks, uint32_t n_tiles, uint4 *d_tiles,
+                                       uint32_t *d_lens, cudaStream_t s);
+cudaError_t launch_build_tiles_ragged(const uint8_t *d_ascii, const uint64_t *d_offs, uint64_t n_reads,
+                                      uint32_t chunks, uint32_t n_tiles, uint4 *d_tiles,
+                                      uint32_t *d_lens, cudaStream_t s);
+
+// scan_kernel.cu
+ScanVariant pick_variant(int k, int forced);
+void build_peq_tables(const uint64_t *kmers, uint32_t n_kmers, int k, ScanVariant v,
+                      std::vector<uint32_t> &table, uint32_t &n_groups);
+cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *launches);
+
+// exact_kernels.cu
+int exact_count_select(Ctx *c, uint8_t k, float lc_adjusted, uint64_t lim, uint64_t solid_km,
+                       const uint64_t *forbidden, uint64_t n_forbidden, std::vector<uint64_t> &kmers,
+                       std::vector<uint64_t> &counts, uint64_t *n_distinct, uint64_t *n_had_n);
+
+// peak_kernels.cu
+cudaError_t measure_int_peak(const Ctx &c, double *lop3, double *imad, double *mixed);
+
+} // namespace apc
+
+struct apc_ctx : public apc::Ctx {};

@@ -1,0 +1,311 @@
+// scan_kernel.cu — K1 approx_scan: the approximate-count hot path for sm_100a.
+//
+// Replaces errorCount (/root/reference/approx_counter.cpp:531-601): the SeqAn
+// FM-index search find<0,2>(…, EditDistance()) (:586), the per-level read
+// bitsets (:553-565, :580-582) and their popcount sum (:589-596).  Per
+// (k-mer, read) the reference's result is [d<=0]+[d<=1]+[d<=2] with d the
+// minimum edit distance between the k-mer and any substring of the read
+// (oracle/seqan_model.cpp checks this against the literal
+// search-scheme recursion).
+//
+// Algorithm: bit-parallel Wu–Manber automaton with three error levels.  Bit i
+// of level e says "k-mer prefix of length i+1 matches a suffix of the text
+// read so far with <= e edits".  Per text column:
+//     R0' = ((R0 << 1) | 1) & Eq
+//     Re' = ((Re << 1) & Eq) | R(e-1) | (R(e-1) << 1) | (R(e-1)' << 1) | 1
+// and a read is flagged at level e when bit k-1 of Re was ever set.
+//
+// B200 mapping (integer-pipe bound, no tensor cores, text stays in L2/HBM):
+//  * lane = read.  A warp walks one 32-read tile; its 128-bit tile loads are
+//    fully coalesced and need no shared-memory staging.
+//  * F k-mers are INTERLEAVED in one unit (bit i*F+f = row i of k-mer f), so a
+//    shift by F moves every k-mer one row and the F vacated low bits take the
+//    "| 1" of all F automata with a single multiply-add: R*2^F + (2^F-1).
+//    No carries or cross-field leaks exist, so packing is free:
+//      k<=10: 3 per 32-bit word, k<=16: 2 per word, k<=21: 3 per 64-bit pair.
+//  * the shifts are issued as IMAD (FMA pipe) by passing 2^F as a runtime
+//    operand; the boolean algebra is LOP3 (ALU pipe).  Per unit and column
+//    that is 5 IMAD + 5 LOP3 + 1.5 LOP3 of hit accumulation — both integer
+//    pipes stay busy instead of only the ALU.
+//  * Eq comes from a 5-row x 16-byte match table in shared memory, one
+//    LDS.128 per column per thread (4 state words); the text byte already is
+//    the row offset, so no address arithmetic is spent on it.
+//  * each thread keeps per-k-mer hit counters in registers across all tiles
+//    of its job; one REDUX + one atomicAdd per (k-mer, warp) at the end.
+#include "apc_internal.h"
+
+namespace apc {
+
+constexpr int kMinBlocks = 3;
+
+ScanVariant pick_variant(int k, int forced) {
+    ScanVariant v{1, 1};
+    switch (forced) {
+    case 1: return ScanVariant{1, 1};
+    case 2: if (k <= 16) return ScanVariant{1, 2}; break;
+    case 3: if (k <= 10) return ScanVariant{1, 3}; break;
+    case 6: if (k >= 12 && k <= 21) return ScanVariant{2, 3}; break;
+    default: break;
+    }
+    if (k <= 10) v = ScanVariant{1, 3};
+    else if (k <= 16) v = ScanVariant{1, 2};
+    else if (k <= 21) v = ScanVariant{2, 3};
+    return v;
+}
+
+// Match tables: table[g][c][w] for group g, base c (0..3; row 4 = N stays 0),
+// thread word w.  k-mer q sits in group q / QG, unit (q % QG) / F, field
+// (q % QG) % F; row i (i-th base of the k-mer, :70-78 order) is bit i*F+f of
+// the unit.
+void build_peq_tables(const uint64_t *kmers, uint32_t n_kmers, int k, ScanVariant v,
+                      std::vector<uint32_t> &table, uint32_t &n_groups) {
+    const uint32_t qg = v.queries_per_group();
+    n_groups = (n_kmers + qg - 1) / qg;
+    table.assign((size_t)n_groups * kPeqRows * kWordsPerThread, 0u);
+    for (uint32_t q = 0; q < n_kmers; q++) {
+        const uint32_t g = q / qg, r = q % qg, u = r / v.f, f = r % v.f;
+        uint32_t *t = table.data() + (size_t)g * kPeqRows * kWordsPerThread;
+        for (int i = 0; i < k; i++) {
+            const uint32_t c = (kmers[q] >> (2 * (k - 1 - i))) & 3;
+            const uint32_t bit = i * v.f + f;
+            t[c * kWordsPerThread + u * v.nw + bit / 32] |= 1u << (bit % 32);
+        }
+    }
+}
+
+// ---- text columns for the four state words of a thread --------------------------
+// core() advances the automaton by one column and returns the new levels in
+// n0/n1/n2 (also stored to r0/r1/r2).  Hit accumulation is separate so that
+// two columns share one 3-input OR per level (acc |= nA | nB = one LOP3).
+// Boolean steps are pinned to one LOP3 each (inline PTX is opaque to nvcc's
+// re-association, which otherwise regroups the OR chains into 8 LOP3 per column
+// instead of 6.5).  LUT = f(0xF0, 0xCC, 0xAA).
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
+__device__ __forceinline__ uint32_t and2(uint32_t a, uint32_t b) { return lop3<0xC0>(a, b, 0u); }       // a & b
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) { return lop3<0xEA>(a, b, c); } // (a & b) | c
+__device__ __forceinline__ uint32_t or3(uint32_t a, uint32_t b, uint32_t c) { return lop3<0xFE>(a, b, c); }    // a | b | c
+
+template <int NW>
+struct Column;
+
+template <>
+struct Column<1> {
+    // one unit per word
+    static __device__ __forceinline__ void core(uint32_t (&r0)[4], uint32_t (&r1)[4], uint32_t (&r2)[4],
+                                                const uint4 eq4, const uint32_t mul, const uint32_t m) {
+        const uint32_t eq[4] = {eq4.x, eq4.y, eq4.z, eq4.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t a = r0[u] * mul + m;  // (R0 << F) | 1s
+            const uint32_t n0 = and2(a, eq[u]);
+            const uint32_t s1 = r1[u] * mul + m; // (R1 << F) | 1s
+            const uint32_t d0 = n0 * mul;        // R0' << F
+            const uint32_t n1 = or3(and_or(s1, eq[u], r0[u]), a, d0);
+            const uint32_t s2 = r2[u] * mul;     // R2 << F
+            const uint32_t d1 = n1 * mul;        // R1' << F
+            const uint32_t n2 = or3(and_or(s2, eq[u], r1[u]), s1, d1);
+            r0[u] = n0; r1[u] = n1; r2[u] = n2;
+        }
+    }
+};
+
+template <>
+struct Column<2> {
+    // two units of 64 bits: words (0,1) and (2,3) as (lo,hi)
+    static __device__ __forceinline__ void shl(uint32_t lo, uint32_t hi, uint32_t mul, uint32_t add,
+                                               uint32_t &olo, uint32_t &ohi) {
+        const unsigned long long t = (unsigned long long)lo * mul + add; // IMAD.WIDE
+        olo = (uint32_t)t;
+        ohi = hi * mul + (uint32_t)(t >> 32);
+    }
+    static __device__ __forceinline__ void core(uint32_t (&r0)[4], uint32_t (&r1)[4], uint32_t (&r2)[4],
+                                                const uint4 eq4, const uint32_t mul, const uint32_t m) {
+        const uint32_t eq[4] = {eq4.x, eq4.y, eq4.z, eq4.w};
+#pragma unroll
+        for (int u = 0; u < 4; u += 2) {
+            uint32_t al, ah, s1l, s1h, d0l, d0h, s2l, s2h, d1l, d1h;
+            shl(r0[u], r0[u + 1], mul, m, al, ah);
+            const uint32_t n0l = and2(al, eq[u]), n0h = and2(ah, eq[u + 1]);
+            shl(r1[u], r1[u + 1], mul, m, s1l, s1h);
+            shl(n0l, n0h, mul, 0u, d0l, d0h);
+            const uint32_t n1l = or3(and_or(s1l, eq[u], r0[u]), al, d0l);
+            const uint32_t n1h = or3(and_or(s1h, eq[u + 1], r0[u + 1]), ah, d0h);
+            shl(r2[u], r2[u + 1], mul, 0u, s2l, s2h);
+            shl(n1l, n1h, mul, 0u, d1l, d1h);
+            const uint32_t n2l = or3(and_or(s2l, eq[u], r1[u]), s1l, d1l);
+            const uint32_t n2h = or3(and_or(s2h, eq[u + 1], r1[u + 1]), s1h, d1h);
+            r0[u] = n0l; r0[u + 1] = n0h;
+            r1[u] = n1l; r1[u + 1] = n1h;
+            r2[u] = n2l; r2[u + 1] = n2h;
+        }
+    }
+};
+
+// One column, accumulate immediately (tail columns).
+template <int NW>
+__device__ __forceinline__ void step1(uint32_t (&r0)[4], uint32_t (&r1)[4], uint32_t (&r2)[4],
+                                      uint32_t (&a0)[4], uint32_t (&a1)[4], uint32_t (&a2)[4],
+                                      const uint4 eq, const uint32_t mul, const uint32_t m) {
+    Column<NW>::core(r0, r1, r2, eq, mul, m);
+#pragma unroll
+    for (int w = NW - 1; w < 4; w += NW) { // row k-1 lives in the last word of a unit
+        a0[w] |= r0[w]; a1[w] |= r1[w]; a2[w] |= r2[w];
+    }
+}
+
+// Two columns, one 3-input OR per level and word.
+template <int NW>
+__device__ __forceinline__ void step2(uint32_t (&r0)[4], uint32_t (&r1)[4], uint32_t (&r2)[4],
+                                      uint32_t (&a0)[4], uint32_t (&a1)[4], uint32_t (&a2)[4],
+                                      const uint4 eqa, const uint4 eqb, const uint32_t mul, const uint32_t m) {
+    Column<NW>::core(r0, r1, r2, eqa, mul, m);
+    uint32_t p0[4], p1[4], p2[4];
+#pragma unroll
+    for (int w = 0; w < 4; w++) { p0[w] = r0[w]; p1[w] = r1[w]; p2[w] = r2[w]; }
+    Column<NW>::core(r0, r1, r2, eqb, mul, m);
+#pragma unroll
+    for (int w = NW - 1; w < 4; w += NW) {
+        a0[w] = or3(a0[w], p0[w], r0[w]);
+        a1[w] = or3(a1[w], p1[w], r1[w]);
+        a2[w] = or3(a2[w], p2[w], r2[w]);
+    }
+}
+
+__device__ __forceinline__ uint4 lds_row(const uint32_t *table, const uint32_t off) {
+    return *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(table) + off);
+}
+
+__device__ __forceinline__ uint4 ldg_tile(const uint4 *p) { return __ldg(p); }
+
+template <int NW, int F>
+__global__ void __launch_bounds__(kScanWarps * 32, kMinBlocks)
+approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, const uint32_t chunks,
+                   const uint32_t read_len, const uint32_t *__restrict__ peq, const uint32_t n_groups,
+                   const uint32_t tiles_per_job, const uint32_t mul, const uint32_t top_shift,
+                   unsigned long long *__restrict__ counts) {
+    constexpr int UNITS = kWordsPerThread / NW;
+    constexpr int ACC0 = NW - 1; // word of a unit that holds row k-1
+    __shared__ __align__(16) uint32_t s_peq[kPeqRows * kWordsPerThread];
+
+    const uint32_t g = blockIdx.x % n_groups;
+    const uint32_t job = blockIdx.x / n_groups;
+    if (threadIdx.x < kPeqRows * kWordsPerThread)
+        s_peq[threadIdx.x] = peq[(size_t)g * kPeqRows * kWordsPerThread + threadIdx.x];
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tile_begin = job * tiles_per_job;
+    const uint32_t tile_end = min(n_tiles, tile_begin + tiles_per_job);
+    const uint32_t m = mul - 1;
+    const uint32_t full = read_len / kChunkBases, rem = read_len % kChunkBases;
+
+    uint32_t cnt[UNITS * F];
+#pragma unroll
+    for (int i = 0; i < UNITS * F; i++) cnt[i] = 0;
+
+    for (uint32_t tile = tile_begin + warp; tile < tile_end; tile += kScanWarps) {
+        uint32_t r0[4], r1[4], r2[4], a0[4], a1[4], a2[4];
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            const bool low = (NW == 1) || ((w & 1) == 0);
+            r0[w] = 0;
+            r1[w] = low ? m : 0;            // prefix 1 by one deletion
+            r2[w] = low ? (m * mul + m) : 0; // prefixes 1..2 by deletions
+            a0[w] = r0[w]; a1[w] = r1[w]; a2[w] = r2[w];
+        }
+        const uint4 *p = tiles + (size_t)tile * chunks * kTileReads + lane;
+        uint4 v = ldg_tile(p);
+        for (uint32_t ch = 0; ch < full; ch++) {
+            const uint4 nxt = (ch + 1 < chunks) ? ldg_tile(p + (size_t)(ch + 1) * kTileReads) : v;
+            const uint32_t tw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+                const uint32_t o0 = tw[wi] & 0xFFu, o1 = __byte_perm(tw[wi], 0u, 0x4441u);
+                const uint32_t o2 = __byte_perm(tw[wi], 0u, 0x4442u), o3 = tw[wi] >> 24;
+                step2<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, o0), lds_row(s_peq, o1), mul, m);
+                step2<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, o2), lds_row(s_peq, o3), mul, m);
+            }
+            v = nxt;
+        }
+        if (rem) {
+            const uint32_t tw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if ((uint32_t)(wi * 4 + j) < rem) {
+                        const uint32_t off = (j == 0) ? (tw[wi] & 0xFFu)
+                                           : (j == 3) ? (tw[wi] >> 24)
+                                                      : __byte_perm(tw[wi], 0u, 0x4440u + j);
+                        step1<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, off), mul, m);
+                    }
+                }
+            }
+        }
+        // hits of this read: [d<=0] + [d<=1] + [d<=2] per k-mer (:589-593)
+#pragma unroll
+        for (int u = 0; u < UNITS; u++) {
+            const int w = u * NW + ACC0;
+#pragma unroll
+            for (int f = 0; f < F; f++) {
+                const uint32_t sh = top_shift + f;
+                cnt[u * F + f] += ((a0[w] >> sh) & 1u) + ((a1[w] >> sh) & 1u) + ((a2[w] >> sh) & 1u);
+            }
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < UNITS * F; i++) {
+        const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, cnt[i]);
+        if (lane == 0 && total)
+            atomicAdd(&counts[(size_t)g * (UNITS * F) + i], (unsigned long long)total);
+    }
+}
+
+template <int NW, int F>
+static cudaError_t launch_variant(const Ctx &c, unsigned long long *d_counts, uint32_t tiles_per_job) {
+    const uint32_t jobs = (c.n_tiles + tiles_per_job - 1) / tiles_per_job;
+    const uint64_t grid = (uint64_t)jobs * c.n_groups;
+    if (grid == 0 || grid > 0x7FFFFFFFull) return grid ? cudaErrorInvalidConfiguration : cudaSuccess;
+    const uint32_t mul = 1u << F;
+    uint32_t top = (uint32_t)(c.k - 1) * F;
+    if (NW == 2) top -= 32; // relative to the high word
+    approx_scan_kernel<NW, F><<<(unsigned)grid, kScanWarps * 32, 0, c.stream>>>(
+        c.d_tiles, c.n_tiles, c.chunks, c.max_len, c.d_peq, c.n_groups, tiles_per_job, mul, top, d_counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *launches) {
+    const size_t n_slots = (size_t)c.n_groups * c.variant.queries_per_group();
+    *launches = 0;
+    if (n_slots == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(d_counts, 0, n_slots * sizeof(unsigned long long), c.stream);
+    if (e != cudaSuccess) return e;
+    if (c.n_tiles == 0 || c.max_len == 0) return cudaSuccess;
+
+    uint32_t tpj = (uint32_t)c.opt_tiles_per_job;
+    if (tpj == 0) {
+        // aim for >= 16 waves of (SMs x resident CTAs) when the problem allows it,
+        // never less than one tile per warp
+        const uint64_t target = (uint64_t)c.sm_count * kMinBlocks * 16;
+        const uint64_t work = (uint64_t)c.n_tiles * c.n_groups;
+        uint64_t t = work / (target ? target : 1);
+        t = (t / kScanWarps) * kScanWarps;
+        if (t < kScanWarps) t = kScanWarps;
+        if (t > 1024) t = 1024;
+        tpj = (uint32_t)t;
+    }
+    *launches = 1;
+    if (c.variant.nw == 1 && c.variant.f == 1) return launch_variant<1, 1>(c, d_counts, tpj);
+    if (c.variant.nw == 1 && c.variant.f == 2) return launch_variant<1, 2>(c, d_counts, tpj);
+    if (c.variant.nw == 1 && c.variant.f == 3) return launch_variant<1, 3>(c, d_counts, tpj);
+    if (c.variant.nw == 2 && c.variant.f == 3) return launch_variant<2, 3>(c, d_counts, tpj);
+    return cudaErrorInvalidValue;
+}
+
+} // namespace apc

@@ -1,0 +1,148 @@
+/*
+ * apc.h — C ABI of libapc, the B200 (sm_100a) implementation of
+ * approx_counter's counting path.
+ *
+ * The reference (qbonenfant/approx_counter, one C++ translation unit) has no
+ * plugin / FFI layer: its hot path is two static functions called from main().
+ * This header is the boundary a maintainer would bind instead of those calls;
+ * each entry point cites the reference code it replaces
+ * (/root/reference/approx_counter.cpp:line).  INTEGRATION.md shows the patch.
+ *
+ * Conventions: plain C types, caller-owned HOST buffers unless a parameter is
+ * documented as a device pointer, `int` status return (APC_OK or a negative
+ * APC_ERR_*), no exceptions cross the ABI.  One apc_ctx drives one GPU; a
+ * context is not re-entrant (one call at a time per context).  There is no
+ * CPU fallback: without a usable CUDA device apc_create fails.
+ *
+ * k-mers are 2-bit packed exactly like the reference's dna2int (:55-62):
+ * A=0 C=1 G=2 T=3, first base in the most significant used bits, k <= 32.
+ */
+#ifndef APC_H
+#define APC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APC_VERSION 1
+
+#define APC_OK 0
+#define APC_ERR_INVALID (-1)    /* bad argument (NULL, k outside [2,32], ...) */
+#define APC_ERR_CUDA (-2)       /* a CUDA runtime call failed; see apc_last_error */
+#define APC_ERR_NO_DEVICE (-3)  /* no CUDA device / device index out of range */
+#define APC_ERR_NO_SAMPLE (-4)  /* a stage needs apc_upload_sample first */
+#define APC_ERR_NO_QUERIES (-5) /* apc_scan before apc_set_queries */
+#define APC_ERR_NOMEM (-6)      /* host or device allocation failed */
+#define APC_ERR_CAPACITY (-7)   /* caller-provided output capacity too small */
+#define APC_MAXERR 2            /* compile-time edit bound, reference :25 */
+
+typedef struct apc_ctx apc_ctx;
+
+/* Per-stage device times of the most recent calls, CUDA events on the
+ * context's stream, milliseconds. */
+typedef struct apc_timing {
+    float upload_ms;  /* H2D + layout kernel of apc_upload_sample        */
+    float exact_ms;   /* apc_exact_topn device work                      */
+    float scan_ms;    /* approximate-count kernel(s) of the last scan    */
+    float total_ms;   /* whole last apc_approx_count incl. H2D/D2H       */
+    uint64_t scan_launches; /* kernels launched by the last scan         */
+} apc_timing;
+
+int apc_version(void);
+const char *apc_strerror(int status);
+/* number of visible CUDA devices, or a negative APC_ERR_* */
+int apc_device_count(void);
+
+/* Bind a context to CUDA device `device` and create its stream.  Replaces
+ * nothing in the reference (which is CPU/OpenMP, :547); this is the one-time
+ * set-up a host adds before the per-end loop (:858). */
+int apc_create(int device, apc_ctx **out);
+void apc_destroy(apc_ctx *ctx);
+/* Text of the last failure on this context ("" if none). */
+const char *apc_last_error(const apc_ctx *ctx);
+/* Run subsequent work on an existing cudaStream_t (e.g. a torch stream) so
+ * the caller can bracket it with its own events.  NULL = context's stream. */
+int apc_set_stream(apc_ctx *ctx, void *cuda_stream);
+int apc_sync(apc_ctx *ctx);
+
+/* ---- the sampled text ------------------------------------------------------
+ * Replaces the `sequence_set_type sample` that sampleSequences returns (:415,
+ * :867) and errorCount indexes (:537-541): instead of a SeqAn FM index the
+ * sampled read ends live in HBM as scan tiles (32 reads, column-major, one
+ * pre-scaled code byte per base; N and padding never match).
+ * `bases`: ASCII, row-major, n_reads x read_len (sl for starts, sl+1 for
+ * ends, :463/:466).  Letters other than ACGTacgt are N (Dna5, :38). */
+int apc_upload_sample(apc_ctx *ctx, const uint8_t *bases, uint64_t n_reads,
+                      uint32_t read_len);
+/* Ragged form: read r is bases[offsets[r] .. offsets[r+1]). */
+int apc_upload_sample_ragged(apc_ctx *ctx, const uint8_t *bases,
+                             const uint64_t *offsets, uint64_t n_reads);
+int apc_sample_info(const apc_ctx *ctx, uint64_t *n_reads, uint32_t *max_len,
+                    uint64_t *total_bases);
+
+/* ---- exact count + filter + top-N -------------------------------------------
+ * Replaces count_kmers (:487-519, called :874) followed by get_most_frequent
+ * (:396-405, called :898): counts every N-free window of the uploaded sample
+ * that passes the low-complexity filter (:214-234, float32 `>=`, threshold
+ * already adjusted by :183-186) and is not in `forbidden` (:330-332), then
+ * returns the first `lim` k-mers in CompareCount order (:275-305: count desc,
+ * complexity asc, k-mer value desc).  kmers_out/counts_out hold >= lim
+ * entries; *n_out = number written.  n_distinct/n_had_n (optional) receive
+ * count.size() (:883) and the skipped-window tally (:506). */
+int apc_exact_topn(apc_ctx *ctx, uint8_t k, float lc_adjusted, uint64_t lim,
+                   const uint64_t *forbidden, uint64_t n_forbidden,
+                   uint64_t *kmers_out, uint64_t *counts_out, uint64_t *n_out,
+                   uint64_t *n_distinct, uint64_t *n_had_n);
+/* Replaces get_solid_kmers (:372-388, called :892): every k-mer with count >=
+ * solid_km, in CompareCount order (the reference leaves ties unspecified).
+ * Returns APC_ERR_CAPACITY (and the needed size in *n_out) if capacity is
+ * too small. */
+int apc_exact_solid(apc_ctx *ctx, uint8_t k, float lc_adjusted, uint64_t solid_km,
+                    const uint64_t *forbidden, uint64_t n_forbidden,
+                    uint64_t *kmers_out, uint64_t *counts_out, uint64_t capacity,
+                    uint64_t *n_out, uint64_t *n_distinct, uint64_t *n_had_n);
+
+/* ---- approximate count: the hot path ------------------------------------------
+ * Replaces errorCount (:531-601, called :922) minus its index build: for each
+ * k-mer, counts_out[i] = sum over e=0..2 of the number of sampled reads
+ * flagged at error level e (:553-565, :589-596), i.e. sum over reads of
+ * max(0, 3 - d) with d the minimum edit distance between the k-mer and any
+ * substring of the read (text N matches nothing).  Only the k-mer values are
+ * read, as in :584.  Host in, host out; H2D/D2H inside the call. */
+int apc_approx_count(apc_ctx *ctx, uint8_t k, const uint64_t *kmers,
+                     uint32_t n_kmers, uint64_t *counts_out);
+
+/* Split-phase form of the same call for resident data and multi-GPU use:
+ * set_queries uploads the match tables, scan launches the kernel on the
+ * context's stream (asynchronous; d_counts is a DEVICE pointer to n_kmers
+ * uint64 that the kernel overwrites, or NULL to use the context's own
+ * buffer), get_counts synchronises and copies the context's buffer back.
+ * A multi-GPU host scans one read shard per GPU and sums the count vectors
+ * (one all-reduce of n_kmers uint64 — see INTEGRATION.md). */
+int apc_set_queries(apc_ctx *ctx, uint8_t k, const uint64_t *kmers,
+                    uint32_t n_kmers);
+int apc_scan(apc_ctx *ctx, uint64_t *d_counts);
+int apc_get_counts(apc_ctx *ctx, uint64_t *counts_out);
+/* Device address of the context's own count buffer (n_kmers uint64). */
+uint64_t *apc_counts_device_ptr(apc_ctx *ctx);
+
+int apc_last_timing(const apc_ctx *ctx, apc_timing *out);
+
+/* Tuning / test knobs.  "scan_variant": 0 auto, 1 = one k-mer per 32-bit
+ * word, 2 = two per word (k<=16), 3 = three per word (k<=10), 6 = three per
+ * 64-bit pair (k<=21).  "tiles_per_job": reads-tiles per CTA (0 auto). */
+int apc_set_option(apc_ctx *ctx, const char *name, int64_t value);
+
+/* Integer-pipe peak microbenchmark (roofline denominator):
+ * runs dependent-free LOP3 / IMAD / mixed chains on every SM and returns
+ * warp-level lane-ops per second for each. */
+int apc_measure_int_peak(apc_ctx *ctx, double *lop3_ops_per_s,
+                         double *imad_ops_per_s, double *mixed_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APC_H */

@@ -1,0 +1,148 @@
+"""GPU parity of the approximate-count kernel (K1) against the CPU oracle,
+through the C ABI (apc_upload_sample / apc_approx_count)."""
+import numpy as np
+import pytest
+
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+ACGT = np.frombuffer(b"ACGT", np.uint8)
+ADAPTER = b"AATGTACTTCGTTCAGTTACGTATTGCT"
+
+
+def mutate(rng, s, n_edits):
+    m = list(s)
+    for _ in range(n_edits):
+        op = rng.integers(0, 3)
+        p = int(rng.integers(0, max(1, len(m))))
+        if op == 0 and m:
+            m[p] = int(rng.choice(ACGT))
+        elif op == 1 and m:
+            del m[p]
+        else:
+            m.insert(p, int(rng.choice(ACGT)))
+    return bytes(m)
+
+
+def make_sample(rng, n, L, k, p_n=0.002):
+    sample = rng.choice(ACGT, size=(n, L))
+    for r in range(n):
+        if rng.random() < 0.7:
+            m = mutate(rng, ADAPTER, int(rng.integers(0, 5)))[: L]
+            pos = int(rng.integers(0, L - len(m) + 1)) if rng.random() < 0.7 else int(rng.choice([0, L - len(m)]))
+            sample[r, pos:pos + len(m)] = np.frombuffer(m, np.uint8)
+    mask = rng.random((n, L)) < p_n
+    sample[mask] = ord("N")
+    return sample
+
+
+def make_kmers(rng, k, n_random):
+    ks = []
+    src = (ADAPTER * 3)
+    for i in range(0, len(ADAPTER)):
+        ks.append(orc.dna2int(src[i:i + k].decode()))
+    for _ in range(n_random):
+        ks.append(int.from_bytes(rng.bytes(8), "little") & ((1 << (2 * k)) - 1))
+    return np.array(ks, np.uint64)
+
+
+@pytest.mark.parametrize("k", [4, 8, 10, 11, 12, 15, 16, 17, 20, 21, 22, 27, 31, 32])
+def test_parity_all_k(counter, k):
+    rng = np.random.default_rng(100 + k)
+    n, L = 257, 101
+    sample = make_sample(rng, n, L, k)
+    kmers = make_kmers(rng, k, 37)
+    counter.set_option("scan_variant", 0)
+    counter.upload_sample(sample)
+    got = counter.errorCount(kmers, k)
+    codes, offs = orc.encode_matrix(sample)
+    want = orc.error_count(codes, offs, kmers, k, fast=True)
+    assert np.array_equal(got, want)
+    assert got.max() > 0
+
+
+@pytest.mark.parametrize("k,variant", [(8, 1), (8, 2), (8, 3), (16, 1), (16, 2), (12, 6), (16, 6), (20, 1), (20, 6)])
+def test_variants_agree(counter, k, variant):
+    rng = np.random.default_rng(7 * k + variant)
+    sample = make_sample(rng, 200, 64, k)
+    kmers = make_kmers(rng, k, 11)
+    counter.upload_sample(sample)
+    counter.set_option("scan_variant", variant)
+    try:
+        got = counter.errorCount(kmers, k)
+    finally:
+        counter.set_option("scan_variant", 0)
+    codes, offs = orc.encode_matrix(sample)
+    want = orc.error_count(codes, offs, kmers, k, fast=True)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("L", [1, 7, 15, 16, 17, 31, 32, 33, 100, 101, 150, 151, 200, 201])
+def test_read_lengths(counter, L):
+    rng = np.random.default_rng(L)
+    k = min(16, max(2, L))
+    sample = make_sample(rng, 70, L, k) if L >= len(ADAPTER) else rng.choice(ACGT, size=(70, L))
+    kmers = make_kmers(rng, k, 5)
+    counter.upload_sample(sample)
+    got = counter.errorCount(kmers, k)
+    codes, offs = orc.encode_matrix(sample)
+    want = orc.error_count(codes, offs, kmers, k, fast=True)
+    assert np.array_equal(got, want)
+
+
+def test_ragged_and_empty_reads(counter):
+    rng = np.random.default_rng(5)
+    k = 12
+    reads = []
+    for i in range(150):
+        L = int(rng.integers(0, 90))
+        reads.append(bytes(rng.choice(ACGT, size=L)))
+    reads[3] = ADAPTER
+    reads[4] = b""
+    reads[5] = ADAPTER[:11]
+    reads[6] = b"N" * 40
+    kmers = make_kmers(rng, k, 9)
+    counter.upload_sample(reads)
+    got = counter.errorCount(kmers, k)
+    codes, offs = orc.encode(reads)
+    want = orc.error_count(codes, offs, kmers, k, fast=True)
+    assert np.array_equal(got, want)
+
+
+def test_appendix_b_vectors(counter):
+    reads = ["TTACGTTGCATT", "TTACGTAGCATT", "TTACGTGCATT", "TTACGTTTGCATT", "TTACCTTGGATT", "TTACGNTGCATT",
+             "GGGGGGGGGGGG", "ACGTTGCA", "CGTTGC", "ACGTTG", "TTAGGTTCCATT"]
+    counter.upload_sample(reads)
+    assert counter.errorCount([orc.dna2int("ACGTTGCA")], 8).tolist() == [18]
+    reads = ["GGAATGTACTTCGTTCAGTTACG", "GGAATGTACTTCGTCAGTTACGT", "AATGTACTTAGTTCAGCC", "AATGAACTTAGTTCAGCC",
+             "CCAATGTACTTTCGTTCAAGAA", "AATGTACTTCGTTC", "TTTTTTTTTTTTTTTTTTTT"]
+    counter.upload_sample(reads)
+    assert counter.errorCount([orc.dna2int("AATGTACTTCGTTCAG")], 16).tolist() == [10]
+
+
+def test_no_reads_no_kmers(counter):
+    counter.upload_sample(np.zeros((0, 50), np.uint8))
+    assert counter.errorCount([1, 2, 3], 8).tolist() == [0, 0, 0]
+    counter.upload_sample(np.full((10, 50), ord("A"), np.uint8))
+    assert len(counter.errorCount([], 8)) == 0
+
+
+def test_many_kmers_many_reads_split_phase(counter):
+    """config-1 shape (10k reads x 100, k=16, 500 k-mers) through the resident API."""
+    rng = np.random.default_rng(11)
+    n, L, k = 10000, 100, 16
+    sample = make_sample(rng, n, L, k, p_n=1e-4)
+    kmers = make_kmers(rng, k, 500 - len(ADAPTER))
+    counter.upload_sample(sample)
+    counter.set_queries(kmers, k)
+    counter.scan()
+    got = counter.get_counts()
+    counter.scan()  # idempotent: counts are overwritten, not accumulated
+    again = counter.get_counts()
+    codes, offs = orc.encode_matrix(sample)
+    want = orc.error_count(codes, offs, kmers, k, fast=True)
+    assert np.array_equal(got, want)
+    assert np.array_equal(again, want)
+    t = counter.timing()
+    assert t["scan_ms"] > 0 and t["scan_launches"] == 1

@@ -1,0 +1,27 @@
+"""Scratch timing of the scan kernel on random data (not the contract bench)."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from approx_counter_b200 import ApproxCounter
+
+def run(c, n, L, k, q, variant=0, tpj=0, reps=5):
+    rng = np.random.default_rng(1)
+    sample = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=(n, L))
+    kmers = rng.integers(0, 1 << 62, q).astype(np.uint64) & np.uint64((1 << (2 * k)) - 1)
+    c.set_option("scan_variant", variant); c.set_option("tiles_per_job", tpj)
+    c.upload_sample(sample); c.set_queries(kmers, k)
+    best = 1e9
+    for _ in range(reps):
+        c.scan(); c.sync(); best = min(best, c.timing()["scan_ms"])
+    cols = q * n * L
+    return {"n": n, "L": L, "k": k, "q": q, "variant": variant, "tpj": tpj, "ms": round(best, 4),
+            "Tcol_s": round(cols / best / 1e9, 3), "GCUPS": round(k * cols / best / 1e6, 1)}
+
+if __name__ == "__main__":
+    with ApproxCounter(0) as c:
+        print(json.dumps(c.measure_int_peak()))
+        for args in [(10000, 100, 16, 500), (100000, 100, 16, 2000), (100000, 101, 16, 2000),
+                     (100000, 100, 16, 2000, 1), (200000, 150, 20, 2000), (200000, 150, 20, 2000, 1),
+                     (200000, 200, 32, 2000), (100000, 100, 10, 2000), (100000, 100, 16, 2000, 0, 8),
+                     (100000, 100, 16, 2000, 0, 64), (100000, 100, 16, 2000, 0, 512)]:
+            print(json.dumps(run(c, *args)), flush=True)
