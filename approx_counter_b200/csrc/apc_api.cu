@@ -333,6 +333,15 @@ int apc_set_option(apc_ctx *c, const char *name, int64_t value) {
         c->opt_tiles_per_job = (int)value;
         return APC_OK;
     }
+    if (!std::strcmp(name, "scan_first_read")) {
+        if (value < 0 || value % apc::kTileReads) return apc::fail(c, APC_ERR_INVALID, "scan_first_read must be a multiple of 32");
+        c->opt_first_read = (uint64_t)value;
+        return APC_OK;
+    }
+    if (!std::strcmp(name, "scan_n_reads")) {
+        c->opt_n_reads = value < 0 ? -1 : value;
+        return APC_OK;
+    }
     return apc::fail(c, APC_ERR_INVALID, "unknown option");
 }
 

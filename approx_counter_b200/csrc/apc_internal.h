@@ -76,6 +76,8 @@ struct Ctx {
     // options
     int opt_variant = 0;
     int opt_tiles_per_job = 0;
+    uint64_t opt_first_read = 0;  // scan only reads [first, first+n) of the resident sample
+    int64_t opt_n_reads = -1;     // -1 = to the end
 
     apc_timing timing{};
 };

@@ -1,0 +1,344 @@
+// host_util.cpp — see host_util.h.  Citations: /root/reference/approx_counter.cpp:line.
+#include "host_util.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+#include <random>
+
+namespace apch {
+
+static const char DNA[4] = {'A', 'C', 'G', 'T'}; // :22
+
+bool dna2int(const char *seq, uint32_t k, uint64_t &out) { // :55-62
+    if (k > 32) return false;
+    uint64_t value = 0;
+    for (uint32_t i = 0; i < k; i++) {
+        uint64_t c;
+        switch (seq[i]) {
+        case 'A': case 'a': c = 0; break;
+        case 'C': case 'c': c = 1; break;
+        case 'G': case 'g': c = 2; break;
+        case 'T': case 't': c = 3; break;
+        default: return false;
+        }
+        value = value << 2 | c;
+    }
+    out = value;
+    return true;
+}
+
+std::string int2dna(uint64_t value, uint32_t k) { // :70-78
+    std::string seq(k, 'A');
+    for (uint32_t i = 0; i < k; i++) {
+        seq[k - 1 - i] = DNA[value & 3];
+        value >>= 2;
+    }
+    return seq;
+}
+
+float adjust_threshold(float c_old, uint8_t k_old, uint8_t k_new) { // :183-186
+    float c_new = c_old * float(std::pow(k_new - 2 + 1, 2) / std::pow(k_old - 2 + 1, 2));
+    return c_new;
+}
+
+uint32_t dimer_sum(uint64_t kmer, uint8_t k) { // :216-231
+    uint32_t counts[16] = {0};
+    for (int i = 0; i < k - 1; i++) {
+        counts[kmer & 15]++;
+        kmer >>= 2;
+    }
+    uint32_t sum = 0;
+    for (uint32_t v : counts) sum += v * (v - 1);
+    return sum;
+}
+
+float get_complexity(uint64_t kmer, uint8_t k) { // :247-267
+    float s = dimer_sum(kmer, k) / float(2 * (k - 2));
+    return s;
+}
+
+bool have_low_complexity(uint64_t kmer, uint8_t k, float threshold) { // :214-234
+    return get_complexity(kmer, k) >= threshold;
+}
+
+uint32_t lc_min_filtered_sum(uint8_t k, float threshold) {
+    // dimer sums are <= 31*30 = 930; the quotient is monotone in the numerator
+    for (uint32_t s = 0; s <= 1024; s++) {
+        float q = s / float(2 * (k - 2));
+        if (q >= threshold) return s;
+    }
+    return 0xFFFFFFFFu;
+}
+
+bool CompareCount::operator()(const std::pair<uint64_t, uint64_t> &a,
+                              const std::pair<uint64_t, uint64_t> &b) const { // :283-302
+    if (a.second == b.second) {
+        float a_comp = get_complexity(a.first, (uint8_t)k);
+        float b_comp = get_complexity(b.first, (uint8_t)k);
+        if (a_comp == b_comp) return a.first > b.first;
+        return a_comp < b_comp;
+    }
+    return a.second > b.second;
+}
+
+void get_most_frequent(pair_vector &v, uint64_t limit, int k) { // :396-405
+    if (k <= 2) {
+        // k == 2 makes the score 0/0 = NaN and the reference comparator stops being a
+        // strict weak order; break those ties by k-mer value so the result is defined.
+        std::sort(v.begin(), v.end(), [](const auto &a, const auto &b) {
+            return a.second != b.second ? a.second > b.second : a.first > b.first;
+        });
+    } else {
+        std::sort(v.begin(), v.end(), CompareCount(k));
+    }
+    if (v.size() > limit) v.resize(limit);
+}
+
+bool export_counter(const pair_vector &v, uint8_t k, const std::string &path) { // :157-174
+    std::ofstream f(path);
+    if (!f.is_open()) {
+        fprintf(stderr, "/!\\ ERROR: COULD NOT OPEN FILE %s\n", path.c_str());
+        return false;
+    }
+    std::string buf;
+    buf.reserve(v.size() * (k + 12));
+    for (const auto &p : v) {
+        buf += int2dna(p.first, k);
+        buf += '\t';
+        buf += std::to_string(p.second);
+        buf += '\n';
+    }
+    f.write(buf.data(), (std::streamsize)buf.size());
+    f.close();
+    return true;
+}
+
+bool parse_kmer_list(const std::string &path, std::vector<uint64_t> &out) { // :340-364
+    std::ifstream f(path);
+    if (!f.is_open()) return false;
+    for (std::string line; std::getline(f, line);) {
+        while (!line.empty() && (line.back() == '\r' || line.back() == ' ' || line.back() == '\t')) line.pop_back();
+        if (line.empty() || line.size() > 32) continue;
+        uint64_t v;
+        if (dna2int(line.c_str(), (uint32_t)line.size(), v)) out.push_back(v); // only true DNA k-mers :353
+    }
+    return true;
+}
+
+bool parse_config(const std::string &path, std::vector<std::pair<std::string, std::string>> &out) { // :103-135
+    std::ifstream f(path);
+    if (!f.is_open()) {
+        fprintf(stderr, "/!\\ WARNING: Could not open config file\n");
+        return false;
+    }
+    for (std::string line; std::getline(f, line);) {
+        std::string arg, val;
+        bool sep = false;
+        if (!line.empty() && line[0] == '#') continue;
+        for (char c : line) {
+            if (c == '=') sep = true;
+            else if (c != ' ' && c != '\r') (sep ? val : arg) += c;
+        }
+        out.emplace_back(arg, val); // the reference also records empty lines as ""="" (:127)
+    }
+    return true;
+}
+
+// ---- FASTA / FASTQ ---------------------------------------------------------------
+bool read_fastx(const std::string &path, Reads &out, std::string &err) {
+    FILE *f = fopen(path.c_str(), "rb");
+    if (!f) {
+        err = "could not open " + path;
+        return false;
+    }
+    std::string data;
+    {
+        char buf[1 << 16];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof buf, f)) > 0) data.append(buf, n);
+    }
+    fclose(f);
+    out.bases.clear();
+    out.offsets.assign(1, 0);
+    out.bases.reserve(data.size());
+    const char *p = data.data(), *end = p + data.size();
+    auto skip_ws = [&]() { while (p < end && (*p == '\n' || *p == '\r' || *p == ' ' || *p == '\t')) p++; };
+    auto skip_line = [&]() { while (p < end && *p != '\n') p++; if (p < end) p++; };
+    auto take_line = [&](uint64_t &taken) { // append the letters of one line
+        while (p < end && *p != '\n') {
+            if (*p != '\r' && *p != ' ' && *p != '\t') { out.bases.push_back(*p); taken++; }
+            p++;
+        }
+        if (p < end) p++;
+    };
+    skip_ws();
+    if (p >= end) return true; // empty file: no records
+    const char first = *p;
+    if (first != '>' && first != '@') {
+        err = "unrecognised sequence file format (expected FASTA '>' or FASTQ '@')";
+        return false;
+    }
+    while (p < end) {
+        skip_ws();
+        if (p >= end) break;
+        if (first == '>') {
+            if (*p != '>') { err = "malformed FASTA record"; return false; }
+            skip_line();
+            uint64_t n = 0;
+            while (p < end && *p != '>') take_line(n);
+        } else {
+            if (*p != '@') { err = "malformed FASTQ record"; return false; }
+            skip_line();
+            uint64_t n = 0;
+            while (p < end && *p != '+') take_line(n);
+            if (p >= end) { err = "truncated FASTQ record"; return false; }
+            skip_line(); // '+' line
+            uint64_t q = 0;
+            while (p < end && q < n) { // quality may contain '@' and '>' — count characters
+                while (p < end && *p != '\n') { if (*p != '\r') q++; p++; }
+                if (p < end) p++;
+            }
+        }
+        out.offsets.push_back(out.bases.size());
+    }
+    return true;
+}
+
+// ---- sampling --------------------------------------------------------------------
+std::vector<uint8_t> sample_sequences(const Reads &reads, uint64_t nb_sample, uint64_t cut, bool bot,
+                                      int64_t seed, uint64_t &n_sampled, uint32_t &row_len) { // :415-476
+    const uint64_t n = reads.size();
+    std::vector<int> vec(n);
+    std::iota(vec.begin(), vec.end(), 0);
+    std::mt19937 g;
+    if (seed < 0) {
+        std::random_device rd; // :427-428
+        g.seed(rd());
+    } else {
+        g.seed((uint32_t)seed);
+    }
+    std::shuffle(vec.begin(), vec.end(), g); // :429
+    row_len = (uint32_t)(cut + (bot ? 1 : 0));
+    std::vector<uint8_t> sample;
+    sample.reserve((size_t)std::min<uint64_t>(nb_sample, n) * row_len);
+    uint64_t nb_seq = 0, i = 0;
+    while (nb_seq < nb_sample && i < n) { // :447
+        const uint64_t id = (uint64_t)vec[i];
+        const uint64_t len = reads.length(id);
+        if (cut > 0 && len >= cut * 2) { // :461 (current_cut_size == cut_size here)
+            const char *s = reads.seq(id);
+            if (bot) sample.insert(sample.end(), s + (len - 1 - cut), s + len); // suffix(seq, len-1-cut) :463
+            else sample.insert(sample.end(), s, s + cut);                       // prefix(seq, cut) :466
+            nb_seq++;
+        }
+        i++;
+    }
+    n_sampled = nb_seq;
+    return sample;
+}
+
+// ---- synthetic reads -------------------------------------------------
+namespace {
+struct Rng { // splitmix64-seeded xoshiro256**, raw outputs only
+    uint64_t s[4];
+    static uint64_t splitmix(uint64_t &x) {
+        uint64_t z = (x += 0x9e3779b97f4a7c15ULL);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        return z ^ (z >> 31);
+    }
+    Rng(uint64_t seed, uint64_t index) {
+        uint64_t x = seed * 0xd1342543de82ef95ULL + index * 0x9e3779b97f4a7c15ULL + 0x2545f4914f6cdd1dULL;
+        for (auto &v : s) v = splitmix(x);
+    }
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    uint64_t next() {
+        const uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
+        return r;
+    }
+};
+const char ADAPTER_START[] = "AATGTACTTCGTTCAGTTACGTATTGCT";
+const char ADAPTER_END[] = "GCAATACGTAACTGAACGAAGT";
+
+std::string error_channel(Rng &g, const char *adapter) { // sub 3 %, ins 2 %, del 3 % per base
+    std::string m;
+    for (const char *p = adapter; *p; p++) {
+        const uint64_t r = g.next() % 100;
+        if (r < 3) {
+            int b = (int)(strchr("ACGT", *p) - "ACGT");
+            m += "ACGT"[(b + 1 + g.next() % 3) & 3];
+        } else if (r < 5) {
+            m += "ACGT"[g.next() & 3];
+            m += *p;
+        } else if (r < 8) {
+            // deleted
+        } else {
+            m += *p;
+        }
+    }
+    return m;
+}
+} // namespace
+
+std::string synth_read(uint64_t seed, uint64_t index, uint32_t sl) {
+    Rng g(seed, index);
+    const uint64_t len = 2ull * sl + 50 + g.next() % 400;
+    std::string s(len, 'A');
+    for (uint64_t i = 0; i < len; i++) {
+        const uint64_t r = g.next();
+        s[i] = (r % 10000 == 0) ? 'N' : "ACGT"[(r >> 20) & 3];
+    }
+    if (g.next() % 10 != 0) { // 90 % of reads carry both adapters
+        const uint64_t off_s = g.next() % 8;
+        const std::string a = error_channel(g, ADAPTER_START);
+        if (off_s + a.size() <= len) s.replace(off_s, a.size(), a);
+        const uint64_t off_e = g.next() % 8;
+        const std::string b = error_channel(g, ADAPTER_END);
+        if (off_e + b.size() <= len) s.replace(len - off_e - b.size(), b.size(), b);
+    }
+    return s;
+}
+
+void synth_ends(uint64_t seed, uint64_t first, uint64_t n, uint32_t sl, bool bot, uint8_t *out) {
+    const uint32_t row = sl + (bot ? 1 : 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        const std::string s = synth_read(seed, first + (uint64_t)i, sl);
+        const char *src = bot ? s.data() + (s.size() - 1 - sl) : s.data();
+        memcpy(out + (size_t)i * row, src, row);
+    }
+}
+
+bool synth_write(const std::string &path, uint64_t seed, uint64_t n, uint32_t sl, bool fastq) {
+    FILE *f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    std::string buf;
+    for (uint64_t i = 0; i < n; i++) {
+        const std::string s = synth_read(seed, i, sl);
+        buf += fastq ? '@' : '>';
+        buf += 'r';
+        buf += std::to_string(i);
+        buf += '\n';
+        buf += s;
+        buf += '\n';
+        if (fastq) {
+            buf += "+\n";
+            buf.append(s.size(), 'I');
+            buf += '\n';
+        }
+        if (buf.size() > (1u << 22)) {
+            fwrite(buf.data(), 1, buf.size(), f);
+            buf.clear();
+        }
+    }
+    fwrite(buf.data(), 1, buf.size(), f);
+    fclose(f);
+    return true;
+}
+
+} // namespace apch

@@ -184,7 +184,8 @@ __device__ __forceinline__ uint4 ldg_tile(const uint4 *p) { return __ldg(p); }
 
 template <int NW, int F>
 __global__ void __launch_bounds__(kScanWarps * 32, kMinBlocks)
-approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, const uint32_t chunks,
+approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, const uint64_t n_reads,
+                   const uint32_t chunks,
                    const uint32_t read_len, const uint32_t *__restrict__ peq, const uint32_t n_groups,
                    const uint32_t tiles_per_job, const uint32_t mul, const uint32_t top_shift,
                    unsigned long long *__restrict__ counts) {
@@ -247,7 +248,10 @@ approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, cons
                 }
             }
         }
-        // hits of this read: [d<=0] + [d<=1] + [d<=2] per k-mer (:589-593)
+        // hits of this read: [d<=0] + [d<=1] + [d<=2] per k-mer (:589-593); lanes past
+        // the last read of a partial tile hold padding and must not count (k <= 2
+        // matches the empty string)
+        if ((uint64_t)tile * kTileReads + lane >= n_reads) continue;
 #pragma unroll
         for (int u = 0; u < UNITS; u++) {
             const int w = u * NW + ACC0;
@@ -267,16 +271,23 @@ approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, cons
     }
 }
 
+struct ScanRange {
+    const uint4 *tiles; // first tile of the range
+    uint32_t n_tiles;
+    uint64_t n_reads;   // reads in the range (relative to its first tile)
+};
+
 template <int NW, int F>
-static cudaError_t launch_variant(const Ctx &c, unsigned long long *d_counts, uint32_t tiles_per_job) {
-    const uint32_t jobs = (c.n_tiles + tiles_per_job - 1) / tiles_per_job;
+static cudaError_t launch_variant(const Ctx &c, const ScanRange &r, unsigned long long *d_counts,
+                                  uint32_t tiles_per_job) {
+    const uint32_t jobs = (r.n_tiles + tiles_per_job - 1) / tiles_per_job;
     const uint64_t grid = (uint64_t)jobs * c.n_groups;
     if (grid == 0 || grid > 0x7FFFFFFFull) return grid ? cudaErrorInvalidConfiguration : cudaSuccess;
     const uint32_t mul = 1u << F;
     uint32_t top = (uint32_t)(c.k - 1) * F;
     if (NW == 2) top -= 32; // relative to the high word
     approx_scan_kernel<NW, F><<<(unsigned)grid, kScanWarps * 32, 0, c.stream>>>(
-        c.d_tiles, c.n_tiles, c.chunks, c.max_len, c.d_peq, c.n_groups, tiles_per_job, mul, top, d_counts);
+        r.tiles, r.n_tiles, r.n_reads, c.chunks, c.max_len, c.d_peq, c.n_groups, tiles_per_job, mul, top, d_counts);
     return cudaGetLastError();
 }
 
@@ -287,13 +298,22 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
     cudaError_t e = cudaMemsetAsync(d_counts, 0, n_slots * sizeof(unsigned long long), c.stream);
     if (e != cudaSuccess) return e;
     if (c.n_tiles == 0 || c.max_len == 0) return cudaSuccess;
+    // optional sub-range of the resident sample (multi-GPU hosts give every GPU one shard)
+    const uint64_t first = c.opt_first_read < c.n_reads ? c.opt_first_read : c.n_reads;
+    uint64_t count = c.n_reads - first;
+    if (c.opt_n_reads >= 0 && (uint64_t)c.opt_n_reads < count) count = (uint64_t)c.opt_n_reads;
+    if (count == 0) return cudaSuccess;
+    ScanRange r;
+    r.tiles = c.d_tiles + (size_t)(first / kTileReads) * c.chunks * kTileReads;
+    r.n_tiles = (uint32_t)((count + kTileReads - 1) / kTileReads);
+    r.n_reads = count;
 
     uint32_t tpj = (uint32_t)c.opt_tiles_per_job;
     if (tpj == 0) {
         // aim for >= 16 waves of (SMs x resident CTAs) when the problem allows it,
         // never less than one tile per warp
         const uint64_t target = (uint64_t)c.sm_count * kMinBlocks * 16;
-        const uint64_t work = (uint64_t)c.n_tiles * c.n_groups;
+        const uint64_t work = (uint64_t)r.n_tiles * c.n_groups;
         uint64_t t = work / (target ? target : 1);
         t = (t / kScanWarps) * kScanWarps;
         if (t < kScanWarps) t = kScanWarps;
@@ -301,10 +321,10 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
         tpj = (uint32_t)t;
     }
     *launches = 1;
-    if (c.variant.nw == 1 && c.variant.f == 1) return launch_variant<1, 1>(c, d_counts, tpj);
-    if (c.variant.nw == 1 && c.variant.f == 2) return launch_variant<1, 2>(c, d_counts, tpj);
-    if (c.variant.nw == 1 && c.variant.f == 3) return launch_variant<1, 3>(c, d_counts, tpj);
-    if (c.variant.nw == 2 && c.variant.f == 3) return launch_variant<2, 3>(c, d_counts, tpj);
+    if (c.variant.nw == 1 && c.variant.f == 1) return launch_variant<1, 1>(c, r, d_counts, tpj);
+    if (c.variant.nw == 1 && c.variant.f == 2) return launch_variant<1, 2>(c, r, d_counts, tpj);
+    if (c.variant.nw == 1 && c.variant.f == 3) return launch_variant<1, 3>(c, r, d_counts, tpj);
+    if (c.variant.nw == 2 && c.variant.f == 3) return launch_variant<2, 3>(c, r, d_counts, tpj);
     return cudaErrorInvalidValue;
 }
 
