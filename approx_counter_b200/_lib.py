@@ -23,7 +23,8 @@ _vp = C.c_void_p
 
 class ApcTiming(C.Structure):
     _fields_ = [("upload_ms", C.c_float), ("exact_ms", C.c_float), ("scan_ms", C.c_float),
-                ("total_ms", C.c_float), ("scan_launches", C.c_uint64)]
+                ("total_ms", C.c_float), ("scan_launches", C.c_uint64),
+                ("exact_launches", C.c_uint64)]
 
 
 SYMBOLS = {

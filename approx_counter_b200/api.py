@@ -55,8 +55,14 @@ class ApproxCounter:
         self.close()
 
     def set_stream(self, cuda_stream):
-        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.Stream().cuda_stream) or None."""
-        self._check(self._lib.apc_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else 0)))
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream), or
+        None for the context's own stream.  0 is torch's spelling of the legacy default
+        stream and is passed on as cudaStreamLegacy."""
+        if cuda_stream is None:
+            handle = 0
+        else:
+            handle = int(cuda_stream) or 1  # cudaStreamLegacy == (cudaStream_t)0x1
+        self._check(self._lib.apc_set_stream(self._h, C.c_void_p(handle)))
 
     def sync(self):
         self._check(self._lib.apc_sync(self._h))
@@ -136,6 +142,10 @@ class ApproxCounter:
         self._n_kmers = len(km)
         self._check(self._lib.apc_set_queries(self._h, int(k), km.ctypes.data, len(km)))
 
+    def set_queries_ptr(self, kmers_ptr, n_kmers, k):
+        self._n_kmers = int(n_kmers)
+        self._check(self._lib.apc_set_queries(self._h, int(k), C.c_void_p(int(kmers_ptr)), int(n_kmers)))
+
     def scan(self, d_counts_ptr=None):
         """Launch the scan on the context's stream (asynchronous)."""
         self._check(self._lib.apc_scan(self._h, C.c_void_p(int(d_counts_ptr) if d_counts_ptr else 0)))
@@ -152,7 +162,8 @@ class ApproxCounter:
         t = ApcTiming()
         self._check(self._lib.apc_last_timing(self._h, C.byref(t)))
         return {"upload_ms": t.upload_ms, "exact_ms": t.exact_ms, "scan_ms": t.scan_ms,
-                "total_ms": t.total_ms, "scan_launches": int(t.scan_launches)}
+                "total_ms": t.total_ms, "scan_launches": int(t.scan_launches),
+                "exact_launches": int(t.exact_launches)}
 
     def measure_int_peak(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

@@ -131,6 +131,7 @@ void apc_destroy(apc_ctx *c) {
     cudaFree(c->d_counts);
     cudaFree(c->d_stage);
     cudaFree(c->d_stage_offs);
+    apc::free_exact_scratch(c);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -224,8 +225,14 @@ static int exact_common(apc_ctx *c, uint8_t k, float lc, uint64_t lim, uint64_t 
     if (!c->has_sample) return apc::fail(c, APC_ERR_NO_SAMPLE, "exact stage: no sample uploaded");
     if (!n_out || (!forbidden && n_forbidden)) return apc::fail(c, APC_ERR_INVALID, "NULL argument");
     std::vector<uint64_t> km, ct;
-    if ((st = apc::exact_count_select(c, k, lc, lim, solid_km, forbidden, n_forbidden, km, ct, n_distinct, n_had_n)))
-        return st;
+    uint64_t needed = 0;
+    st = apc::exact_count_select(c, k, lc, lim, solid_km, forbidden, n_forbidden, capacity, km, ct, &needed,
+                                 n_distinct, n_had_n);
+    if (st == APC_ERR_CAPACITY) {
+        *n_out = needed;
+        return apc::fail(c, APC_ERR_CAPACITY, "output capacity too small");
+    }
+    if (st) return st;
     *n_out = km.size();
     if (km.size() > capacity) return apc::fail(c, APC_ERR_CAPACITY, "output capacity too small");
     if (!km.empty() && (!kmers_out || !counts_out)) return apc::fail(c, APC_ERR_INVALID, "NULL output");

@@ -34,6 +34,24 @@ struct ScanVariant {
     int queries_per_group() const { return f * kWordsPerThread / nw; }
 };
 
+// device scratch of the exact stage (exact_kernels.cu); grown on demand, kept
+// across calls so the per-end loop does not re-allocate
+struct ExactScratch {
+    void *d_keys_a = nullptr;  size_t keys_a_cap = 0;  // key stream, later the unique keys
+    void *d_keys_b = nullptr;  size_t keys_b_cap = 0;  // sorted keys
+    void *d_temp = nullptr;    size_t temp_cap = 0;    // cub temp storage
+    uint32_t *d_start = nullptr; size_t start_cap = 0; // run starts, d+1 entries
+    uint16_t *d_dsum = nullptr;  size_t dsum_cap = 0;  // dimer sums of the unique keys
+    uint32_t *d_block_a = nullptr; size_t block_a_cap = 0;
+    uint32_t *d_block_b = nullptr; size_t block_b_cap = 0;
+    unsigned long long *d_hist = nullptr; size_t hist_cap = 0;
+    unsigned long long *d_counters = nullptr; size_t counters_cap = 0;
+    uint64_t *d_forb = nullptr; size_t forb_cap = 0;
+    uint64_t *d_sel_k = nullptr; size_t sel_k_cap = 0;
+    uint64_t *d_sel_c = nullptr; size_t sel_c_cap = 0;
+    uint64_t launches = 0;
+};
+
 struct Ctx {
     int device = -1;
     int sm_count = 0;
@@ -80,6 +98,13 @@ struct Ctx {
     int64_t opt_n_reads = -1;     // -1 = to the end
 
     apc_timing timing{};
+    ExactScratch exact;
+
+    // upper bound of the number of k-windows of the resident sample (:496)
+    uint64_t total_windows(uint32_t k) const {
+        if (uniform_len) return max_len >= k ? n_reads * (uint64_t)(max_len - k + 1) : 0;
+        return total_bases;
+    }
 };
 
 int fail(Ctx *c, int status, const char *what, cudaError_t e = cudaSuccess);
@@ -106,8 +131,10 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
 
 // exact_kernels.cu
 int exact_count_select(Ctx *c, uint8_t k, float lc_adjusted, uint64_t lim, uint64_t solid_km,
-                       const uint64_t *forbidden, uint64_t n_forbidden, std::vector<uint64_t> &kmers,
-                       std::vector<uint64_t> &counts, uint64_t *n_distinct, uint64_t *n_had_n);
+                       const uint64_t *forbidden, uint64_t n_forbidden, uint64_t capacity,
+                       std::vector<uint64_t> &kmers, std::vector<uint64_t> &counts, uint64_t *n_needed,
+                       uint64_t *n_distinct, uint64_t *n_had_n);
+void free_exact_scratch(Ctx *c);
 
 // peak_kernels.cu
 cudaError_t measure_int_peak(const Ctx &c, double *lop3, double *imad, double *mixed);

@@ -188,7 +188,7 @@ approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, cons
                    const uint32_t chunks,
                    const uint32_t read_len, const uint32_t *__restrict__ peq, const uint32_t n_groups,
                    const uint32_t tiles_per_job, const uint32_t mul, const uint32_t top_shift,
-                   unsigned long long *__restrict__ counts) {
+                   const uint32_t n_kmers, unsigned long long *__restrict__ counts) {
     constexpr int UNITS = kWordsPerThread / NW;
     constexpr int ACC0 = NW - 1; // word of a unit that holds row k-1
     __shared__ __align__(16) uint32_t s_peq[kPeqRows * kWordsPerThread];
@@ -266,8 +266,8 @@ approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, cons
 #pragma unroll
     for (int i = 0; i < UNITS * F; i++) {
         const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, cnt[i]);
-        if (lane == 0 && total)
-            atomicAdd(&counts[(size_t)g * (UNITS * F) + i], (unsigned long long)total);
+        const uint32_t slot = g * (UNITS * F) + i; // == index of the k-mer; the last group may be padded
+        if (lane == 0 && total && slot < n_kmers) atomicAdd(&counts[slot], (unsigned long long)total);
     }
 }
 
@@ -287,15 +287,14 @@ static cudaError_t launch_variant(const Ctx &c, const ScanRange &r, unsigned lon
     uint32_t top = (uint32_t)(c.k - 1) * F;
     if (NW == 2) top -= 32; // relative to the high word
     approx_scan_kernel<NW, F><<<(unsigned)grid, kScanWarps * 32, 0, c.stream>>>(
-        r.tiles, r.n_tiles, r.n_reads, c.chunks, c.max_len, c.d_peq, c.n_groups, tiles_per_job, mul, top, d_counts);
+        r.tiles, r.n_tiles, r.n_reads, c.chunks, c.max_len, c.d_peq, c.n_groups, tiles_per_job, mul, top, c.n_kmers, d_counts);
     return cudaGetLastError();
 }
 
 cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *launches) {
-    const size_t n_slots = (size_t)c.n_groups * c.variant.queries_per_group();
     *launches = 0;
-    if (n_slots == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(d_counts, 0, n_slots * sizeof(unsigned long long), c.stream);
+    if (c.n_kmers == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(d_counts, 0, (size_t)c.n_kmers * sizeof(unsigned long long), c.stream);
     if (e != cudaSuccess) return e;
     if (c.n_tiles == 0 || c.max_len == 0) return cudaSuccess;
     // optional sub-range of the resident sample (multi-GPU hosts give every GPU one shard)

@@ -1,0 +1,494 @@
+#!/usr/bin/env python
+"""bench.py — approximate-count throughput of the B200 path (and of the CPU
+reference arm) on BASELINE.json's synthetic workloads.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl b200|reference]
+
+A *step* is one pass of the hot path (errorCount, reference :531-601) over one
+batch: all `lim` query k-mers against the sampled read STARTS (n x sl bases) and
+the sampled read ENDS (n x (sl+1) bases, :463) — what the reference does once
+per run.  Metric: GCUPS = k x Q x (sum of sampled read lengths) / t / 1e9
+(SURVEY.md §8d); `queries_per_s` = 2Q / t rides along.
+
+N > 1 (torchrun, one rank per GPU): weak scaling — every rank holds its own
+n-read shard of the synthetic read stream, scans it for all queries and the
+per-k-mer count vectors are summed with one small NCCL all-reduce per end.
+
+One JSON line on stdout (rank 0).  See DESIGN.md §Measurement for every key.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: reads per GPU, sampled length, k, lim, generator seed
+    "C1": dict(n=10_000, sl=100, k=16, lim=500, seed=1001,
+               text="C1: synthetic 10k ONT-like reads with planted adapters, k=16, -sn 10000 -sl 100 -lim 500"),
+    "C2": dict(n=100_000, sl=100, k=16, lim=2000, seed=1002,
+               text="C2: synthetic 100k ONT-like reads with planted adapters, k=16, -sn 100000 -sl 100 -lim 2000"),
+    "C3": dict(n=1_000_000, sl=150, k=20, lim=5000, seed=1003,
+               text="C3: synthetic 1M reads, k=20, -sn 1000000 -sl 150 -lim 5000"),
+    "C4": dict(n=1_000_000, sl=200, k=32, lim=10000, seed=1004,
+               text="C4: synthetic 1M reads, k=32, -sn 1000000 -sl 200 -lim 10000"),
+}
+PARAM_LC = 1.0          # reference default (:711)
+ALGO_OPS_PER_COLUMN = 16  # Myers/Hyyro column update, the figure builder and judge share
+L2_FLUSH_BYTES = 256 << 20
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks: nvidia-smi sampled DURING the timed region (B200_PROFILING.md "clocks" line)
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, gpu_id):
+        self.rows = []
+        self.proc = None
+        self.err = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_id), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception as e:  # nvidia-smi missing: report, do not invent numbers
+            self.err = repr(e)
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"error": self.err}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.06:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(self.NAMES, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"error": "no nvidia-smi sample fell inside the timed region", "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def make_ends(w, first, pinned_torch=None):
+    """Sampled starts and ends of synthetic reads [first, first+n): uint8[n, sl], uint8[n, sl+1]."""
+    from approx_counter_b200 import host
+    n, sl = w["n"], w["sl"]
+    if pinned_torch is not None:
+        torch = pinned_torch
+        t0 = torch.empty((n, sl), dtype=torch.uint8, pin_memory=True)
+        t1 = torch.empty((n, sl + 1), dtype=torch.uint8, pin_memory=True)
+        a, b = t0.numpy(), t1.numpy()
+        host.synth_ends(w["seed"], first, n, sl, False, a)
+        host.synth_ends(w["seed"], first, n, sl, True, b)
+        return (a, b), (t0, t1)
+    return (host.synth_ends(w["seed"], first, n, sl, False), host.synth_ends(w["seed"], first, n, sl, True)), None
+
+
+def columns_per_step(w, q_start, q_end):
+    return q_start * w["n"] * w["sl"] + q_end * w["n"] * (w["sl"] + 1)
+
+
+def cpu_leg(w, ends, queries, target_s, threads=0):
+    """Time the CPU restatement (oracle/, Myers bit-vector + OpenMP over k-mers, mirroring the
+    reference's `omp for schedule(dynamic)` :567) on the first R reads of both ends."""
+    from oracle import orc
+    k = w["k"]
+    nthreads = orc.num_threads() if threads <= 0 else threads
+
+    def run(r):
+        cols = 0
+        t0 = time.perf_counter()
+        for sample, km in zip(ends, queries):
+            codes, offs = orc.encode_matrix(sample[:r])
+            orc.error_count(codes, offs, km, k, fast=True, nb_thread=nthreads)
+            cols += len(km) * r * sample.shape[1]
+        return time.perf_counter() - t0, cols
+
+    r = min(w["n"], 64)
+    t, cols = run(r)            # calibration: grow until the run is long enough to trust
+    while t < 0.3 and r < w["n"]:
+        r = min(w["n"], r * 4)
+        t, cols = run(r)
+    rate = cols / max(t, 1e-6)
+    per_read = (len(queries[0]) * ends[0].shape[1] + len(queries[1]) * ends[1].shape[1])
+    r = int(max(32, min(w["n"], target_s * rate / max(per_read, 1))))
+    t, cols = run(r)
+    return {"seconds": t, "columns": cols, "reads": r, "threads": nthreads,
+            "gcups": k * cols / t / 1e9, "queries_per_s": (len(queries[0]) + len(queries[1])) / t * (r / w["n"])}
+
+
+def reference_queries(w, ends):
+    """Top-`lim` exact k-mers of each end with the CPU restatement (:874, :898) — set-up of the
+    reference arm only (the B200 arm uses its own exact stage on the GPU)."""
+    from oracle import orc
+    thr = orc.adjust_threshold(PARAM_LC, 16, w["k"])
+    out = []
+    for sample in ends:
+        codes, offs = orc.encode_matrix(sample)
+        keys, cnts, _ = orc.count_kmers(codes, offs, w["k"], thr)
+        km, _ = orc.get_most_frequent(keys, cnts, w["lim"], w["k"])
+        out.append(km)
+    return out
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as g
+    g.build_oracle()
+    t_gen = time.perf_counter()
+    ends, _ = make_ends(w, 0)
+    queries = reference_queries(w, ends)
+    log(f"[reference] workload + queries ready in {time.perf_counter() - t_gen:.1f}s")
+    # bounded sample per step so that warmup+steps stay within a few minutes
+    per_step = max(0.5, min(3.0, 150.0 / max(1, args.steps + args.warmup)))
+    first = cpu_leg(w, ends, queries, per_step)
+    r = first["reads"]
+    from oracle import orc
+    k = w["k"]
+
+    def step():
+        t0 = time.perf_counter()
+        for sample, km in zip(ends, queries):
+            codes, offs = orc.encode_matrix(sample[:r])
+            orc.error_count(codes, offs, km, k, fast=True, nb_thread=first["threads"])
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    total = sum(times)
+    cols = len(queries[0]) * r * ends[0].shape[1] + len(queries[1]) * r * ends[1].shape[1]
+    value = k * cols * args.steps / total / 1e9
+    sample = (f"first {r} of {w['n']} sampled reads of both ends x all {len(queries[0])}+{len(queries[1])} "
+              f"query k-mers per step ({cols:.3g} columns/step)")
+    line = {
+        "impl": "reference", "metric": "approx_count_gcups", "value": value, "unit": "GCUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": w["text"] + ", both ends", "k": k, "reads": w["n"], "sl": w["sl"], "lim": w["lim"],
+                   "seed": w["seed"]},
+        "queries_per_s": (len(queries[0]) + len(queries[1])) * args.steps / total * (r / w["n"]),
+        "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": first["threads"], "kind": "port",
+                         "sample": sample,
+                         "note": "CPU restatement (oracle/apc_oracle.c, Myers bit-vector + OpenMP over k-mers); "
+                                 "the reference binary needs SeqAn, which is absent from this image"},
+        "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus} (one rank per GPU)")
+        raise SystemExit(f"WORLD_SIZE={world} does not match --gpus {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from approx_counter_b200 import ApproxCounter, host, allreduce_counts, load
+    load()  # fails loudly if libapc.so is missing
+    k, n, sl, lim = w["k"], w["n"], w["sl"], w["lim"]
+    stream = torch.cuda.Stream(dev)  # everything below runs on this (non-default) stream
+    torch.cuda.set_stream(stream)
+
+    # ---- inputs: this rank's shard of the synthetic read stream, in pinned host memory
+    (h_start, h_end), pinned = make_ends(w, rank * n, pinned_torch=torch)
+    ends = (h_start, h_end)
+    ctxs = [ApproxCounter(local_rank), ApproxCounter(local_rank)]
+    for c, s in zip(ctxs, ends):
+        c.set_stream(stream.cuda_stream)
+        c.upload_sample_ptr(s.ctypes.data, s.shape[0], s.shape[1])
+
+    # ---- queries: top-`lim` exact k-mers per end from the GPU exact stage (rank 0's shard,
+    # broadcast so that every rank scans for the same k-mers)
+    thr = host.adjust_threshold(PARAM_LC, 16, k)
+    queries, exact_ms = [], []
+    for c in ctxs:
+        km, ct, nd, hn = c.count_kmers_topn(k, thr, lim)
+        exact_ms.append(c.timing()["exact_ms"])
+        t = torch.zeros(lim, dtype=torch.int64, device=dev)
+        cnt = torch.tensor([len(km)], dtype=torch.int64, device=dev)
+        t[: len(km)] = torch.from_numpy(km.view(np.int64)).to(dev)
+        if world > 1:
+            dist.broadcast(t, 0)
+            dist.broadcast(cnt, 0)
+        queries.append(t[: int(cnt.item())].cpu().numpy().view(np.uint64).copy())
+    q_start, q_end = len(queries[0]), len(queries[1])
+    if min(q_start, q_end) == 0:
+        raise SystemExit("bench.py: the exact stage returned no query k-mers")
+    counts = [torch.zeros(len(q), dtype=torch.int64, device=dev) for q in queries]
+    for c, q in zip(ctxs, queries):
+        c.set_queries(q, k)
+
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    launches = [0]
+    kernel_events = []
+
+    def step(record=False):
+        for c, out in zip(ctxs, counts):
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            c.scan(out.data_ptr())
+            if record:
+                e1.record(stream)
+                kernel_events.append((e0, e1))
+            launches[0] += 1
+            allreduce_counts(out)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 0)):
+        flush.zero_()
+        step()
+    barrier()
+
+    # ---- timed region: K steps, device events around every step (the L2 flush between
+    # steps sits outside the event pairs), clocks sampled meanwhile
+    gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    sampler = ClockSampler(gpu_uuid if gpu_uuid.startswith("GPU-") else "GPU-" + gpu_uuid) if rank == 0 else None
+    if sampler is not None:
+        time.sleep(0.12)
+    launches[0] = 0
+    step_events = []
+    t_mark0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step(record=True)
+        e1.record(stream)
+        step_events.append((e0, e1))
+    barrier()
+    t_mark1 = time.perf_counter()
+    clocks = sampler.stop(t_mark0, t_mark1) if sampler is not None else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in step_events)
+    kern_ms = sum(a.elapsed_time(b) for a, b in kernel_events)
+    n_launch = launches[0]
+    t = torch.tensor([dev_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, kern_ms = float(t[0]), float(t[1])
+
+    cols_rank = columns_per_step(w, q_start, q_end)
+    cols_job = cols_rank * world
+    value = k * cols_job * args.steps / (dev_ms / 1e3) / 1e9
+    final_counts = [c.cpu().numpy().view(np.uint64).copy() for c in counts]
+
+    # ---- end to end through the C ABI with HOST buffers: per step, per end, H2D of the
+    # sampled reads + k-mers, scan, (all-reduce), D2H of the counts
+    e2e_steps = max(1, min(args.steps, 20))
+    h_q = [torch.from_numpy(q.view(np.int64)).pin_memory() for q in queries]
+    h_out = [torch.zeros(len(q), dtype=torch.int64).pin_memory() for q in queries]
+
+    def e2e_step():
+        for c, s, q, o, d in zip(ctxs, ends, h_q, h_out, counts):
+            c.upload_sample_ptr(s.ctypes.data, s.shape[0], s.shape[1])
+            if world == 1:
+                c.errorCount_ptr(q.data_ptr(), q.numel(), k, o.data_ptr())
+            else:
+                c.set_queries_ptr(q.data_ptr(), q.numel(), k)
+                c.scan(d.data_ptr())
+                allreduce_counts(d)
+                o.copy_(d, non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t[0])
+    e2e_value = k * cols_job * e2e_steps / e2e_s / 1e9
+    for o, f in zip(h_out, final_counts):
+        if not np.array_equal(o.numpy().view(np.uint64), f):
+            raise SystemExit("bench.py: end-to-end counts differ from the resident-path counts")
+    h2d = int(h_start.nbytes + h_end.nbytes + 8 * (q_start + q_end))
+    d2h = int(8 * (q_start + q_end))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (approx_scan_kernel)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    int_peak = ctxs[0].measure_int_peak()
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    alu_peak = sms * 4 * 16 * sm_max * 1e6  # ALU pipe: 16 lanes/clk/SMSP (B300_MICROARCH.md:85)
+    per_launch_s = kern_ms / 1e3 / max(n_launch, 1)
+    cols_launch = cols_rank / 2.0
+    # no kernel can retire more than one instruction per SMSP per clock; a faster reading means
+    # the event pairs did not contain the kernel (e.g. it ran on another stream)
+    issue_peak = sms * 4 * 32 * sm_max * 1e6
+    if 4.0 * cols_launch / per_launch_s > issue_peak:
+        raise SystemExit("bench.py: implausible kernel time — the timed region did not contain the scan kernel")
+    achieved = ALGO_OPS_PER_COLUMN * cols_launch / per_launch_s
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")))
+        traffic = prof.get(args.workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    hbm_bytes_launch = n * (sl + 0.5) + 80 * ((q_start + 7) // 8) + 8 * q_start  # tiles (1 B/base) + tables + counts
+    roofline = {
+        "bound": "int-alu", "kernel": "approx_scan_kernel", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
+        "unit": "Tint-op/s", "frac": achieved / alu_peak, "traffic": traffic,
+        "peak_source": f"ALU pipe nominal = {sms} SM x 4 SMSP x 16 lanes/clk x {sm_max:.0f} MHz (SURVEY.md §8d)",
+        "algorithmic_ops_per_column": ALGO_OPS_PER_COLUMN, "columns_per_launch": cols_launch,
+        "avg_launch_ms": per_launch_s * 1e3, "launches_timed": n_launch,
+        "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
+        "measured_int_peaks_Tops": {kk: v / 1e12 for kk, v in int_peak.items()},
+        "frac_of_measured_lop3_peak": achieved / int_peak["lop3_ops_per_s"],
+        "hbm": {"algorithmic_bytes_per_launch": hbm_bytes_launch,
+                "achieved_gbs": hbm_bytes_launch / per_launch_s / 1e9,
+                "peak_gbs": peaks.get("hbm_gbs"), "note": "text is re-read from L2 by every k-mer group; "
+                "the kernel is integer-issue bound, HBM is idle"},
+        "sm_mhz_during_run": sm_mhz,
+    }
+
+    # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import __graft_entry__ as g
+        g.build_oracle()
+        leg = cpu_leg(w, ends, queries, target_s=args.cpu_seconds)
+        cpu = {"value": leg["gcups"], "unit": "GCUPS", "cores": leg["threads"], "kind": "port",
+               "sample": f"first {leg['reads']} of {n} sampled reads of both ends x all {q_start}+{q_end} query "
+                         f"k-mers ({leg['columns']:.3g} columns, {leg['seconds']:.1f} s wall)",
+               "host_cpus": os.cpu_count(),
+               "note": "CPU restatement of the reference semantics (Myers bit-vector + OpenMP over k-mers); "
+                       "the reference binary itself needs SeqAn, absent from this image"}
+        # the CPU leg doubles as a spot check of the GPU counts on its sample
+        from oracle import orc
+        r = min(leg["reads"], 512)
+        chk = ApproxCounter(local_rank)
+        chk.upload_sample(np.ascontiguousarray(h_start[:r]))
+        got = chk.errorCount(queries[0], k)
+        codes, offs = orc.encode_matrix(h_start[:r])
+        want = orc.error_count(codes, offs, queries[0], k, fast=True)
+        chk.close()
+        if not np.array_equal(got, want):
+            raise SystemExit("bench.py: GPU counts differ from the oracle on the CPU-baseline sample")
+
+    line = {
+        "metric": "approx_count_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": w["text"] + ", both ends (start n x sl, end n x (sl+1))", "k": k,
+                   "reads_per_gpu": n, "sl": sl, "lim": lim, "queries": [q_start, q_end], "seed": w["seed"],
+                   "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset outside the event pairs)",
+                   "parallelism": f"reads sharded over {world} GPU(s), one all-reduce of Q u64 per end"},
+        "queries_per_s": (q_start + q_end) * args.steps / (dev_ms / 1e3),
+        "columns_per_s": cols_job * args.steps / (dev_ms / 1e3),
+        "wall_s_timed_region": t_mark1 - t_mark0,
+        "exact_stage_ms": exact_ms,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                "path": "apc_upload_sample + apc_approx_count (C ABI, pinned host buffers), wall clock"},
+        "gpu_launches": n_launch,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    for c in ctxs:
+        c.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="C2")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size, seconds of CPU work")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+    return run_b200(args, w)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -48,7 +48,8 @@ typedef struct apc_timing {
     float exact_ms;   /* apc_exact_topn device work                      */
     float scan_ms;    /* approximate-count kernel(s) of the last scan    */
     float total_ms;   /* whole last apc_approx_count incl. H2D/D2H       */
-    uint64_t scan_launches; /* kernels launched by the last scan         */
+    uint64_t scan_launches;  /* kernels launched by the last scan        */
+    uint64_t exact_launches; /* kernels launched by the last exact stage */
 } apc_timing;
 
 int apc_version(void);
@@ -64,7 +65,8 @@ void apc_destroy(apc_ctx *ctx);
 /* Text of the last failure on this context ("" if none). */
 const char *apc_last_error(const apc_ctx *ctx);
 /* Run subsequent work on an existing cudaStream_t (e.g. a torch stream) so
- * the caller can bracket it with its own events.  NULL = context's stream. */
+ * the caller can bracket it with its own events.  NULL = the context's own
+ * stream; for the legacy default stream pass cudaStreamLegacy (0x1). */
 int apc_set_stream(apc_ctx *ctx, void *cuda_stream);
 int apc_sync(apc_ctx *ctx);
 

@@ -1,0 +1,154 @@
+"""CPU tests of the host-side C++ the drop-in binary runs (include/apc_host.h),
+checked against the oracle's restatement of the same reference functions."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "approx_counter_b200", "csrc", "approx_counter")
+
+
+@pytest.fixture(scope="module")
+def host(built):
+    from approx_counter_b200 import host
+    return host
+
+
+def test_codec_matches_oracle(host):
+    rng = np.random.default_rng(0)
+    for k in (2, 7, 16, 20, 32):
+        for _ in range(50):
+            v = int.from_bytes(rng.bytes(8), "little") & ((1 << (2 * k)) - 1)
+            s = orc.int2dna(v, k)
+            assert host.int2dna(v, k) == s
+            assert host.dna2int(s) == v
+            assert host.dna2int(s.lower()) == v
+    with pytest.raises(ValueError):
+        host.dna2int("ACGN")
+
+
+def test_threshold_and_filter_match_oracle(host):
+    rng = np.random.default_rng(1)
+    for k in range(3, 33):
+        for lc in (0.5, 1.0, 1.5, 2.25):
+            thr = host.adjust_threshold(lc, 16, k)
+            assert thr == orc.adjust_threshold(lc, 16, k)
+            smin = host.lc_min_filtered_sum(k, thr)
+            for _ in range(40):
+                v = int.from_bytes(rng.bytes(8), "little") & ((1 << (2 * k)) - 1)
+                if rng.random() < 0.3:  # make it repetitive
+                    v &= int(rng.integers(0, 1 << 16)) * 0x0001000100010001 & ((1 << (2 * k)) - 1)
+                assert host.get_complexity(v, k) == orc.get_complexity(v, k)
+                assert host.have_low_complexity(v, k, thr) == orc.have_low_complexity(v, k, thr)
+                # the integer form the device kernels use
+                assert (orc.dimer_sum(v, k) >= smin) == orc.have_low_complexity(v, k, thr)
+
+
+def test_get_most_frequent_matches_oracle(host):
+    rng = np.random.default_rng(2)
+    for k in (4, 16, 32):
+        keys = np.unique(rng.integers(0, 1 << 62, 3000).astype(np.uint64) & np.uint64((1 << (2 * k)) - 1 if k < 32 else (1 << 64) - 1))
+        cnts = rng.integers(1, 4, len(keys)).astype(np.uint64)
+        for lim in (0, 1, 100, 10 ** 6):
+            a = host.get_most_frequent(keys, cnts, lim, k)
+            b = orc.get_most_frequent(keys, cnts, lim, k)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_export_and_kmer_list(host, tmp_path):
+    p = tmp_path / "c.txt"
+    assert host.export_counter([host.dna2int("ACGT"), host.dna2int("GGGG")], [7, 1], 4, p)
+    assert p.read_text() == "ACGT\t7\nGGGG\t1\n"
+    q = tmp_path / "fk.txt"
+    q.write_text("ACGT\nNNNN\nacgt\n\nTTTT\r\n")
+    assert host.parse_kmer_list(q).tolist() == [host.dna2int("ACGT"), host.dna2int("ACGT"), host.dna2int("TTTT")]
+    assert not host.export_counter([1], [1], 4, tmp_path / "no" / "such" / "dir.txt")
+
+
+FASTA = ">r0 some id\nACGTACGTAC\nGGGG\n>r1\nacgtnnRYAC\n>r2\n\n>r3\nTTTT\n"
+FASTQ = "@r0\nACGTACGTACGGGG\n+\nIIIIIIIIIIIIII\n@r1\nacgtnnRYAC\n+r1\n@@@@>>>>++\n@r2\nTTTT\n+\n@III\n"
+
+
+def test_fasta_fastq_reader(host, tmp_path):
+    fa, fq = tmp_path / "x.fa", tmp_path / "x.fq"
+    fa.write_text(FASTA)
+    fq.write_text(FASTQ)
+    r = host.Reads(fa)
+    assert [r.seq(i) for i in range(len(r))] == [b"ACGTACGTACGGGG", b"acgtnnRYAC", b"", b"TTTT"]
+    r = host.Reads(fq)
+    assert [r.seq(i) for i in range(len(r))] == [b"ACGTACGTACGGGG", b"acgtnnRYAC", b"TTTT"]
+    with pytest.raises(OSError):
+        host.Reads(tmp_path / "missing.fa")
+
+
+def test_sampling_matches_oracle(host, tmp_path):
+    rng = np.random.default_rng(4)
+    reads = [bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(rng.integers(5, 80)))) for _ in range(60)]
+    fa = tmp_path / "s.fa"
+    fa.write_text("".join(f">r{i}\n{r.decode()}\n" for i, r in enumerate(reads)))
+    r = host.Reads(fa)
+    cut = 12
+    codes, offs = orc.encode(reads)
+    ident = np.arange(len(reads), dtype=np.uint64)
+    for bot in (False, True):
+        got = r.sample(len(reads), cut, bot, seed=3)       # sn >= #reads: the set is all eligible reads
+        wc, wo = orc.sample_sequences(codes, offs, ident, len(reads), cut, bot)
+        want = np.frombuffer(b"ACGT", np.uint8)[wc].reshape(-1, cut + (1 if bot else 0))
+        assert got.shape == want.shape
+        assert sorted(map(bytes, got)) == sorted(map(bytes, want))
+        few = r.sample(5, cut, bot, seed=3)                # same seed -> same prefix of the walk
+        assert np.array_equal(few, got[:5])
+    a = r.sample(10, cut, False, seed=1)
+    b = r.sample(10, cut, False, seed=2)
+    assert not np.array_equal(a, b)
+
+
+def test_synthetic_reads_are_deterministic(host, tmp_path):
+    a = host.synth_ends(1001, 0, 64, 100, False)
+    b = host.synth_ends(1001, 32, 32, 100, False)
+    assert np.array_equal(a[32:], b)                       # read i depends on (seed, i) only
+    e = host.synth_ends(1001, 0, 64, 100, True)
+    assert a.shape == (64, 100) and e.shape == (64, 101)
+    assert set(np.unique(a)) <= set(b"ACGTN")
+    fa = tmp_path / "syn.fa"
+    host.synth_write(fa, 1001, 64, 100)
+    r = host.Reads(fa)
+    assert len(r) == 64
+    for i in (0, 17, 63):
+        s = r.seq(i)
+        assert len(s) >= 200 and s[:100] == bytes(a[i]) and s[-101:] == bytes(e[i])
+    fq = tmp_path / "syn.fq"
+    host.synth_write(fq, 1001, 64, 100, fastq=True)
+    rq = host.Reads(fq)
+    assert [rq.seq(i) for i in range(64)] == [r.seq(i) for i in range(64)]
+    adapter = b"AATGTACTTCGTTCAG"
+    assert sum(adapter in bytes(row) for row in a) > 10    # planted, partly mutated
+
+
+def run_cli(*args):
+    return subprocess.run([BIN, *args], capture_output=True, text=True, timeout=60)
+
+
+def test_cli_flag_surface_without_gpu(built, tmp_path):
+    """Option parsing and validation mirror the reference (:604-669, :691-790) and need no GPU."""
+    r = run_cli("--help")
+    assert r.returncode == 0
+    for flag in ("-lc", "-sn", "-sl", "-nt", "-k", "-lim", "-mr", "-v", "-e", "-conf", "-fk", "-sk", "-se", "-o"):
+        assert f"{flag}, --" in r.stdout
+    assert run_cli().returncode == 1                        # missing input (:697-698)
+    assert run_cli("-zz", "1", "x.fa").returncode == 1      # unknown option
+    assert run_cli("-k", "abc", "x.fa").returncode == 1     # not an integer
+    fa = tmp_path / "x.fa"
+    fa.write_text(">r\nACGT\n")
+    r = run_cli("-k", "40", str(fa))                        # uncaught std::invalid_argument (:781-783)
+    assert r.returncode != 0 and "kmer size must be between 2 and 32" in r.stderr
+    r = run_cli("-k", "16", "-sl", "10", str(fa))           # (:785-787)
+    assert r.returncode != 0 and "k <= sl" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = run_cli("-k", "4", "-sl", "10", str(fa))
+        assert r.returncode == 2 and "cannot open CUDA device" in r.stderr   # no CPU fallback

@@ -1,0 +1,189 @@
+"""CPU tests of the oracle (oracle/): known-answer vectors, closed form vs the
+literal SeqAn search-scheme model, filter/comparator/sampling restatements.
+The reference holds no tests or fixtures of its own, so the
+vectors are the hand-checkable ones of SURVEY.md App. B plus tests/golden/."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import orc
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
+ACGT = np.frombuffer(b"ACGT", np.uint8)
+
+
+def test_codec_roundtrip():
+    assert orc.dna2int("ACGT") == 0b00011011          # first base most significant (:55-62)
+    assert orc.int2dna(0b00011011, 4) == "ACGT"        # (:70-78)
+    assert orc.dna2int("T" * 32) == (1 << 64) - 1
+    rng = np.random.default_rng(0)
+    for k in (2, 5, 16, 31, 32):
+        for _ in range(20):
+            v = int.from_bytes(rng.bytes(8), "little") & ((1 << (2 * k)) - 1)
+            assert orc.dna2int(orc.int2dna(v, k)) == v
+
+
+@pytest.mark.parametrize("case", GOLD["appendix_b"], ids=lambda c: c["kmer"])
+def test_appendix_b(case):
+    k, km = case["k"], orc.dna2int(case["kmer"])
+    codes, offs = orc.encode(case["reads"])
+    assert int(orc.error_count(codes, offs, [km], k)[0]) == case["total"]
+    assert int(orc.error_count(codes, offs, [km], k, fast=True)[0]) == case["total"]
+    out, flags = orc.seqan_model_error_count(codes, offs, [km], k, want_flags=True)
+    assert int(out[0]) == case["total"]
+    # per read: flagged at every level e >= d (R0 ⊆ R1 ⊆ R2), contribution 3 - d
+    per = flags[0].sum(axis=0).tolist()
+    assert per == case["per_read"]
+    for r, contrib in enumerate(case["per_read"]):
+        d = orc.min_infix_distance(orc.encode([case["reads"][r]])[0], km, k)
+        assert max(0, 3 - d) == contrib
+        assert flags[0][:, r].tolist() == [int(e >= d) for e in range(3)]
+
+
+@pytest.mark.parametrize("case", GOLD["approx"], ids=lambda c: f"k{c['k']}n{len(c['reads'])}")
+def test_golden_approx(case):
+    k = case["k"]
+    kmers = [orc.dna2int(s) for s in case["kmers"]]
+    codes, offs = orc.encode(case["reads"])
+    assert orc.error_count(codes, offs, kmers, k, fast=True).tolist() == case["counts"]
+    if len(case["reads"]) <= 30:
+        assert orc.error_count(codes, offs, kmers, k).tolist() == case["counts"]
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("k", [4, 5, 6, 7, 9, 11, 13, 16, 21])
+def test_closed_form_equals_seqan_model(k, variant):
+    """Σ_r max(0, 3 - d_r) == Σ_e popcount(tcount[e]) of the search-scheme recursion,
+    including hits flush with read borders, reads shorter than k and N in the text."""
+    rng = np.random.default_rng(1000 * variant + k)
+    for trial in range(6):
+        L = int(rng.integers(k - 2, 2 * k + 6))
+        reads, needle = [], rng.choice(ACGT, size=k).tobytes()
+        for r in range(10):
+            n = int(rng.integers(max(0, k - 3), L + 1))
+            body = bytearray(rng.choice(ACGT, size=n).tobytes())
+            if r % 2 == 0 and n >= k:
+                m = bytearray(needle)
+                for _ in range(int(rng.integers(0, 4))):
+                    p = int(rng.integers(0, len(m)))
+                    op = int(rng.integers(0, 3))
+                    if op == 0:
+                        m[p] = int(rng.choice(ACGT))
+                    elif op == 1 and len(m) > 1:
+                        del m[p]
+                    else:
+                        m.insert(p, int(rng.choice(ACGT)))
+                m = m[:n]
+                pos = int(rng.choice([0, n - len(m)]))
+                body[pos:pos + len(m)] = m
+            if r == 3 and n:
+                body[int(rng.integers(0, n))] = ord("N")
+            reads.append(bytes(body))
+        kmers = [orc.dna2int(needle.decode())] + \
+                [int(x) & ((1 << (2 * k)) - 1) for x in rng.integers(0, 1 << 62, 2)]
+        codes, offs = orc.encode(reads)
+        want = orc.error_count(codes, offs, kmers, k)
+        got = orc.seqan_model_error_count(codes, offs, kmers, k, variant=variant)
+        assert np.array_equal(got, want), (k, trial, reads)
+        assert np.array_equal(orc.error_count(codes, offs, kmers, k, fast=True), want)
+
+
+def test_count_invariants():
+    """3|R0| <= count <= 3n, and |R0| = number of READS holding the k-mer verbatim."""
+    rng = np.random.default_rng(3)
+    k = 10
+    reads = [rng.choice(ACGT, size=60).tobytes() for _ in range(200)]
+    needle = reads[0][5:15]
+    for r in range(0, 200, 4):
+        reads[r] = reads[r][:20] + needle + reads[r][30:]
+    codes, offs = orc.encode(reads)
+    got = int(orc.error_count(codes, offs, [orc.dna2int(needle.decode())], k, fast=True)[0])
+    r0 = sum(needle in r for r in reads)
+    assert 3 * r0 <= got <= 3 * len(reads)
+
+
+def test_filter_thresholds_fp32():
+    # smallest dimer sum the fp32 expression (:227-233) rejects, SURVEY.md App. B
+    for lc, table in GOLD["filter_thresholds"].items():
+        for k, want in table.items():
+            k = int(k)
+            thr = orc.adjust_threshold(float(lc), 16, k)
+            sums = [s for s in range(0, 932, 2) if np.float32(s) / np.float32(2 * (k - 2)) >= np.float32(thr)]
+            assert sums[0] == want
+    assert orc.adjust_threshold(1.0, 16, 16) == 1.0
+    assert abs(orc.adjust_threshold(1.0, 16, 20) - 1.6044445) < 1e-6
+    assert abs(orc.adjust_threshold(1.0, 16, 32) - 4.271111) < 1e-6
+
+
+def test_low_complexity_and_dimer_sum():
+    k = 16
+    poly_a = 0
+    assert orc.dimer_sum(poly_a, k) == 15 * 14
+    assert orc.have_low_complexity(poly_a, k, 1.0)
+    ac = orc.dna2int("ACACACACACACACAC")  # 8 AC + 7 CA
+    assert orc.dimer_sum(ac, k) == 8 * 7 + 7 * 6
+    rnd = orc.dna2int("AATGTACTTCGTTCAG")
+    assert not orc.have_low_complexity(rnd, k, 1.0)
+    assert orc.get_complexity(rnd, k) == pytest.approx(orc.dimer_sum(rnd, k) / 28.0)
+    # `>=`: a score exactly on the threshold is filtered (42/28 == 1.5)
+    rng = np.random.default_rng(1)
+    hit = None
+    for _ in range(200000):
+        v = int.from_bytes(rng.bytes(4), "little")
+        if orc.dimer_sum(v, k) == 42:
+            hit = v
+            break
+    assert hit is not None
+    assert orc.have_low_complexity(hit, k, 1.5) and not orc.have_low_complexity(hit, k, 1.5000001)
+
+
+def test_compare_count_order():
+    k = 16
+    a, b = orc.dna2int("AATGTACTTCGTTCAG"), orc.dna2int("ACACACACACACACAC")
+    keys = np.array([a, b, 5, 7], np.uint64)
+    cnts = np.array([3, 3, 9, 3], np.uint64)
+    tk, tc = orc.get_most_frequent(keys, cnts, 10, k)
+    # count desc, then complexity asc (:301), then k-mer value desc (:297)
+    assert tc.tolist() == [9, 3, 3, 3]
+    comp = [orc.get_complexity(int(x), k) for x in tk[1:]]
+    assert comp == sorted(comp)
+    same = np.array([0b0110, 0b1001], np.uint64)  # equal score, equal count
+    tk, _ = orc.get_most_frequent(same, np.array([1, 1], np.uint64), 10, 4)
+    assert tk.tolist() == sorted(same.tolist(), reverse=True)
+    tk, _ = orc.get_most_frequent(keys, cnts, 2, k)
+    assert len(tk) == 2
+
+
+def test_count_kmers_skips_n_and_filters():
+    reads = ["ACGTACGTAC", "ACGTNCGTAC", "AAAAAAAAAA", "ACG"]
+    codes, offs = orc.encode(reads)
+    keys, cnts, had_n = orc.count_kmers(codes, offs, 4, 1e9)
+    d = dict(zip(keys.tolist(), cnts.tolist()))
+    assert had_n == 4                                    # windows 1..4 of read 1 hold the N
+    assert d[orc.dna2int("ACGT")] == 3 and d[orc.dna2int("AAAA")] == 7
+    assert sum(d.values()) == 7 + 3 + 7
+    keys, cnts, _ = orc.count_kmers(codes, offs, 4, 1.0)  # AAAA: sum=6, 6/4=1.5 >= 1 -> filtered
+    assert orc.dna2int("AAAA") not in keys.tolist()
+    keys, cnts, _ = orc.count_kmers(codes, offs, 4, 1e9, forbidden=[orc.dna2int("ACGT")])
+    assert orc.dna2int("ACGT") not in keys.tolist()
+
+
+def test_sample_sequences_off_by_one():
+    reads = ["".join("ACGT"[(i + j) % 4] for j in range(30 + i)) for i in range(6)] + ["ACGTACGT"]
+    codes, offs = orc.encode(reads)
+    perm = np.arange(len(reads), dtype=np.uint64)[::-1].copy()
+    sc, so = orc.sample_sequences(codes, offs, perm, 4, 10, False)
+    lens = np.diff(so).tolist()
+    assert lens == [10, 10, 10, 10]                       # prefix(seq, cut) (:466); short read skipped (:461)
+    ec, eo = orc.sample_sequences(codes, offs, perm, 4, 10, True)
+    assert np.diff(eo).tolist() == [11, 11, 11, 11]       # suffix(seq, len-1-cut) = cut+1 bases (:463)
+    first = reads[5]
+    assert bytes(np.frombuffer(b"ACGT", np.uint8)[ec[:11]]).decode() == first[-11:]
+
+
+def test_export_format(tmp_path):
+    p = tmp_path / "out.txt"
+    assert orc.export_counter([orc.dna2int("ACGT"), orc.dna2int("TTTT")], [12, 3], 4, p)
+    assert p.read_text() == "ACGT\t12\nTTTT\t3\n"        # :165
