@@ -93,7 +93,22 @@ void get_most_frequent(pair_vector &v, uint64_t limit, int k) { // :396-405
             return a.second != b.second ? a.second > b.second : a.first > b.first;
         });
     } else {
-        std::sort(v.begin(), v.end(), CompareCount(k));
+        // same order as std::sort(CompareCount(k)) (:400), with getComplexity evaluated once
+        // per entry instead of twice per comparison
+        struct Item {
+            uint64_t kmer, count;
+            float comp;
+        };
+        std::vector<Item> items(v.size());
+        for (size_t i = 0; i < v.size(); i++) items[i] = {v[i].first, v[i].second, get_complexity(v[i].first, (uint8_t)k)};
+        std::sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+            if (a.count == b.count) {
+                if (a.comp == b.comp) return a.kmer > b.kmer;
+                return a.comp < b.comp;
+            }
+            return a.count > b.count;
+        });
+        for (size_t i = 0; i < v.size(); i++) v[i] = {items[i].kmer, items[i].count};
     }
     if (v.size() > limit) v.resize(limit);
 }

@@ -1,0 +1,151 @@
+"""End-to-end GPU parity: the drop-in `approx_counter` binary (same flags and output
+files as the reference, :604-669 / :835-955) against the oracle pipeline, byte for
+byte, plus the committed golden fixtures through the Python mirror of the API."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "approx_counter_b200", "csrc", "approx_counter")
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vectors.json")))
+
+
+def oracle_files(reads, k, sl, lim, param_lc, tmp, solid=0, forbidden=None):
+    """What the reference writes when every read is sampled (sn >= #reads, :844-848)."""
+    codes, offs = orc.encode(reads)
+    thr = orc.adjust_threshold(param_lc, 16, k)
+    perm = np.arange(len(reads), dtype=np.uint64)
+    out = {}
+    for which, bot in (("start", False), ("end", True)):
+        sc, so = orc.sample_sequences(codes, offs, perm, len(reads), sl, bot)
+        keys, cnts, _ = orc.count_kmers(sc, so, k, thr, forbidden)
+        if solid:
+            tk, tc = orc.get_solid_kmers(keys, cnts, solid, k)
+        else:
+            tk, tc = orc.get_most_frequent(keys, cnts, lim, k)
+        ek = tmp / f"want_exact.{which}"
+        orc.export_counter(tk, tc, k, ek)
+        approx = orc.error_count(sc, so, tk, k, fast=True)
+        ak, ac = orc.get_most_frequent(tk, approx, lim, k)
+        ok = tmp / f"want_out.{which}"
+        orc.export_counter(ak, ac, k, ok)
+        out[which] = (ek.read_bytes(), ok.read_bytes())
+    return out
+
+
+@pytest.mark.parametrize("fastq,k,sl,lim,n", [(False, 16, 100, 200, 3000), (True, 20, 150, 300, 1500),
+                                              (False, 32, 200, 100, 800), (False, 10, 40, 64, 2000)])
+def test_binary_matches_oracle_files(built, tmp_path, fastq, k, sl, lim, n):
+    from approx_counter_b200 import host
+    path = tmp_path / ("reads.fq" if fastq else "reads.fa")
+    host.synth_write(path, 4242 + k, n, sl, fastq=fastq)
+    r = host.Reads(path)
+    reads = [r.seq(i) for i in range(len(r))]
+    assert len(reads) == n
+    out, exact = tmp_path / "out.txt", tmp_path / "exact.txt"
+    p = subprocess.run([BIN, "-k", str(k), "-sn", str(n), "-sl", str(sl), "-lim", str(lim), "-lc", "1.0",
+                        "-e", str(exact), "-o", str(out), "-nt", "4", str(path)],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    want = oracle_files(reads, k, sl, lim, 1.0, tmp_path)
+    for which in ("start", "end"):
+        assert (tmp_path / f"exact.txt_0.{which}").read_bytes() == want[which][0]   # `_<run>` always appended (:837)
+        assert (tmp_path / f"out.txt_0.{which}").read_bytes() == want[which][1]
+    lines = (tmp_path / "out.txt_0.start").read_text().splitlines()
+    assert len(lines) == lim and all(len(x.split("\t")[0]) == k for x in lines)
+    assert "Kmer size:" in p.stdout and "Approximate k-mer count" in p.stdout
+
+
+def test_binary_skip_end_forbidden_and_solid(built, tmp_path):
+    from approx_counter_b200 import host
+    k, sl, n, lim = 16, 100, 1500, 100
+    path = tmp_path / "reads.fa"
+    host.synth_write(path, 99, n, sl)
+    r = host.Reads(path)
+    reads = [r.seq(i) for i in range(n)]
+    fk = tmp_path / "forbidden.txt"
+    forb = ["AATGTACTTCGTTCAG", "ATGTACTTCGTTCAGT"]
+    fk.write_text("\n".join(forb) + "\n")
+    out = tmp_path / "o"
+    p = subprocess.run([BIN, "-k", str(k), "-sn", str(n), "-sl", str(sl), "-lim", str(lim), "-fk", str(fk),
+                        "-se", "-e", str(tmp_path / "e"), "-o", str(out), str(path)], capture_output=True, text=True,
+                       timeout=300)
+    assert p.returncode == 0, p.stderr
+    want = oracle_files(reads, k, sl, lim, 1.0, tmp_path, forbidden=[orc.dna2int(s) for s in forb])
+    assert (tmp_path / "o_0.start").read_bytes() == want["start"][1]
+    assert (tmp_path / "e_0.start").read_bytes() == want["start"][0]
+    assert not (tmp_path / "o_0.end").exists()                       # -se (:943-951)
+    p = subprocess.run([BIN, "-k", str(k), "-sn", str(n), "-sl", str(sl), "-lim", "100000", "-sk", "50",
+                        "-e", str(tmp_path / "se"), "-o", str(tmp_path / "so"), str(path)],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    want = oracle_files(reads, k, sl, 100000, 1.0, tmp_path, solid=50)
+    for which in ("start", "end"):
+        assert (tmp_path / f"se_0.{which}").read_bytes() == want[which][0]
+        assert (tmp_path / f"so_0.{which}").read_bytes() == want[which][1]
+
+
+def test_binary_config_file_and_multi_run(built, tmp_path):
+    from approx_counter_b200 import host
+    path = tmp_path / "reads.fa"
+    host.synth_write(path, 7, 600, 60)
+    conf = tmp_path / "c.conf"
+    conf.write_text("# comment\nk = 12\nsl=60\nsn=600\nlim=50\nmr=2\n")
+    p = subprocess.run([BIN, "-conf", str(conf), "-lim", "40", "-o", str(tmp_path / "m"), str(path)],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    for run in (0, 1):
+        for which in ("start", "end"):
+            lines = (tmp_path / f"m_{run}.{which}").read_text().splitlines()
+            assert len(lines) == 40 and all(len(x.split("\t")[0]) == 12 for x in lines)   # CLI overrides config
+    assert (tmp_path / "m_0.start").read_bytes() == (tmp_path / "m_1.start").read_bytes()  # whole set sampled
+
+
+@pytest.mark.parametrize("case", GOLD["approx"], ids=lambda c: f"k{c['k']}n{len(c['reads'])}")
+def test_golden_approx_vectors(counter, case):
+    counter.upload_sample(case["reads"])
+    got = counter.errorCount([orc.dna2int(s) for s in case["kmers"]], case["k"])
+    assert got.tolist() == case["counts"]
+
+
+@pytest.mark.parametrize("case", GOLD["pipeline"], ids=lambda c: f"k{c['k']}")
+def test_golden_pipeline_vectors(counter, case):
+    from approx_counter_b200 import host
+    k, lim = case["k"], case["lim"]
+    counter.upload_sample(case["reads"])
+    thr = host.adjust_threshold(case["param_lc"], 16, k)
+    km, ct, nd, hn = counter.count_kmers_topn(k, thr, lim)
+    assert nd == case["n_distinct"] and hn == case["had_n"]
+    assert [[host.int2dna(a, k), int(b)] for a, b in zip(km, ct)] == case["exact"]
+    approx = counter.errorCount(km, k)
+    ak, ac = host.get_most_frequent(km, approx, lim, k)
+    assert [[host.int2dna(a, k), int(b)] for a, b in zip(ak, ac)] == case["approx"]
+
+
+def test_sharded_counter_single_rank(built):
+    """ShardedApproxCounter with world size 1 (no process group): torch stream + torch count tensor."""
+    import torch
+    from approx_counter_b200 import ShardedApproxCounter
+    rng = np.random.default_rng(3)
+    sample = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=(1000, 100))
+    sample[::2, 5:21] = np.frombuffer(b"AATGTACTTCGTTCAG", np.uint8)
+    kmers = np.array([orc.dna2int("AATGTACTTCGTTCAG"), orc.dna2int("AATGTACTTCGTTCAT"), 12345], np.uint64)
+    s = ShardedApproxCounter(device=0)
+    try:
+        with torch.cuda.stream(torch.cuda.Stream(0)):
+            lo, hi = s.upload_sample(sample)
+            assert (lo, hi) == (0, 1000)
+            got = s.errorCount(kmers, 16)
+        got_default = s.errorCount(kmers, 16)   # legacy default stream
+    finally:
+        s.close()
+    codes, offs = orc.encode_matrix(sample)
+    want = orc.error_count(codes, offs, kmers, 16, fast=True)
+    assert np.array_equal(got, want) and np.array_equal(got_default, want)
