@@ -112,6 +112,8 @@ int apc_create(int device, apc_ctx **out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_job_counter, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_job_counter, 0, sizeof(unsigned int));
     if (e != cudaSuccess) {
         apc_destroy(c);
         return APC_ERR_CUDA;
@@ -129,6 +131,7 @@ void apc_destroy(apc_ctx *c) {
     cudaFree(c->d_lens);
     cudaFree(c->d_peq);
     cudaFree(c->d_counts);
+    cudaFree(c->d_job_counter);
     cudaFree(c->d_stage);
     cudaFree(c->d_stage_offs);
     apc::free_exact_scratch(c);

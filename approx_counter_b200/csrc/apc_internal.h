@@ -82,6 +82,7 @@ struct Ctx {
     size_t peq_cap = 0;
     unsigned long long *d_counts = nullptr; // [n_groups * queries_per_group]
     size_t counts_cap = 0;
+    unsigned int *d_job_counter = nullptr;  // job queue head of the persistent scan kernel (self re-arming)
 
     // staging
     uint8_t *d_stage = nullptr;

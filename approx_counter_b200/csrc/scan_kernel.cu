@@ -32,6 +32,8 @@
 //    the row offset, so no address arithmetic is spent on it.
 //  * each thread keeps per-k-mer hit counters in registers across all tiles
 //    of its job; one REDUX + one atomicAdd per (k-mer, warp) at the end.
+#include <algorithm>
+
 #include "apc_internal.h"
 
 namespace apc {
@@ -182,92 +184,112 @@ __device__ __forceinline__ uint4 lds_row(const uint32_t *table, const uint32_t o
 
 __device__ __forceinline__ uint4 ldg_tile(const uint4 *p) { return __ldg(p); }
 
+// Persistent warps: the grid is one wave (SMs x resident CTAs); every WARP pulls jobs
+// (tiles_per_job consecutive tiles x one k-mer group) from a global counter, so there is
+// no tail wave, no CTA-wide barrier and no per-CTA prologue.  Jobs are numbered group-fastest:
+// warps running at the same time read the same text tiles (L2 locality when the text
+// outgrows L2).  Each warp owns a 256-byte slot of shared memory for the match table of
+// its current group; the slot index is merged into the table offset by the same PRMT that
+// extracts the text byte, so a column still costs one PRMT + one LDS.128 per thread.
+constexpr int kSlotBytes = 256;
+
 template <int NW, int F>
 __global__ void __launch_bounds__(kScanWarps * 32, kMinBlocks)
 approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, const uint64_t n_reads,
-                   const uint32_t chunks,
-                   const uint32_t read_len, const uint32_t *__restrict__ peq, const uint32_t n_groups,
-                   const uint32_t tiles_per_job, const uint32_t mul, const uint32_t top_shift,
-                   const uint32_t n_kmers, unsigned long long *__restrict__ counts) {
+                   const uint32_t chunks, const uint32_t read_len, const uint32_t *__restrict__ peq,
+                   const uint32_t n_groups, const uint32_t tiles_per_job, const uint32_t n_jobs,
+                   const uint32_t mul, const uint32_t top_shift, const uint32_t n_kmers,
+                   unsigned long long *__restrict__ counts, unsigned int *__restrict__ job_counter) {
     constexpr int UNITS = kWordsPerThread / NW;
     constexpr int ACC0 = NW - 1; // word of a unit that holds row k-1
-    __shared__ __align__(16) uint32_t s_peq[kPeqRows * kWordsPerThread];
-
-    const uint32_t g = blockIdx.x % n_groups;
-    const uint32_t job = blockIdx.x / n_groups;
-    if (threadIdx.x < kPeqRows * kWordsPerThread)
-        s_peq[threadIdx.x] = peq[(size_t)g * kPeqRows * kWordsPerThread + threadIdx.x];
-    __syncthreads();
+    __shared__ __align__(kSlotBytes) uint32_t s_peq[kScanWarps * kSlotBytes / 4];
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tile_begin = job * tiles_per_job;
-    const uint32_t tile_end = min(n_tiles, tile_begin + tiles_per_job);
+    const uint32_t total_warps = gridDim.x * kScanWarps;
     const uint32_t m = mul - 1;
     const uint32_t full = read_len / kChunkBases, rem = read_len % kChunkBases;
+    uint32_t *const slot = s_peq + warp * (kSlotBytes / 4);
 
-    uint32_t cnt[UNITS * F];
-#pragma unroll
-    for (int i = 0; i < UNITS * F; i++) cnt[i] = 0;
-
-    for (uint32_t tile = tile_begin + warp; tile < tile_end; tile += kScanWarps) {
-        uint32_t r0[4], r1[4], r2[4], a0[4], a1[4], a2[4];
-#pragma unroll
-        for (int w = 0; w < 4; w++) {
-            const bool low = (NW == 1) || ((w & 1) == 0);
-            r0[w] = 0;
-            r1[w] = low ? m : 0;            // prefix 1 by one deletion
-            r2[w] = low ? (m * mul + m) : 0; // prefixes 1..2 by deletions
-            a0[w] = r0[w]; a1[w] = r1[w]; a2[w] = r2[w];
+    for (;;) {
+        uint32_t job = 0;
+        if (lane == 0) {
+            job = atomicAdd(job_counter, 1u);
+            // every warp fails exactly once, so the fetch numbered n_jobs + total_warps - 1 is
+            // the last of this launch: it re-arms the counter for the next one
+            if (job == n_jobs + total_warps - 1u) atomicExch(job_counter, 0u);
         }
-        const uint4 *p = tiles + (size_t)tile * chunks * kTileReads + lane;
-        uint4 v = ldg_tile(p);
-        for (uint32_t ch = 0; ch < full; ch++) {
-            const uint4 nxt = (ch + 1 < chunks) ? ldg_tile(p + (size_t)(ch + 1) * kTileReads) : v;
-            const uint32_t tw[4] = {v.x, v.y, v.z, v.w};
+        job = __shfl_sync(0xFFFFFFFFu, job, 0);
+        if (job >= n_jobs) break;
+        const uint32_t tb = job / n_groups, g = job - tb * n_groups;
+        __syncwarp();
+        if (lane < kPeqRows * kWordsPerThread) slot[lane] = __ldg(peq + (size_t)g * kPeqRows * kWordsPerThread + lane);
+        __syncwarp();
+        const uint32_t tile_begin = tb * tiles_per_job;
+        const uint32_t tile_end = min(n_tiles, tile_begin + tiles_per_job);
+
+        uint32_t cnt[UNITS * F];
 #pragma unroll
-            for (int wi = 0; wi < 4; wi++) {
-                const uint32_t o0 = tw[wi] & 0xFFu, o1 = __byte_perm(tw[wi], 0u, 0x4441u);
-                const uint32_t o2 = __byte_perm(tw[wi], 0u, 0x4442u), o3 = tw[wi] >> 24;
-                step2<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, o0), lds_row(s_peq, o1), mul, m);
-                step2<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, o2), lds_row(s_peq, o3), mul, m);
+        for (int i = 0; i < UNITS * F; i++) cnt[i] = 0;
+
+        for (uint32_t tile = tile_begin; tile < tile_end; tile++) {
+            uint32_t r0[4], r1[4], r2[4], a0[4], a1[4], a2[4];
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const bool low = (NW == 1) || ((w & 1) == 0);
+                r0[w] = 0;
+                r1[w] = low ? m : 0;            // prefix 1 by one deletion
+                r2[w] = low ? (m * mul + m) : 0; // prefixes 1..2 by deletions
+                a0[w] = r0[w]; a1[w] = r1[w]; a2[w] = r2[w];
             }
-            v = nxt;
-        }
-        if (rem) {
-            const uint32_t tw[4] = {v.x, v.y, v.z, v.w};
+            const uint4 *p = tiles + (size_t)tile * chunks * kTileReads + lane;
+            uint4 v = ldg_tile(p);
+            for (uint32_t ch = 0; ch < full; ch++) {
+                const uint4 nxt = (ch + 1 < chunks) ? ldg_tile(p + (size_t)(ch + 1) * kTileReads) : v;
+                const uint32_t tw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int wi = 0; wi < 4; wi++) {
+                for (int wi = 0; wi < 4; wi++) {
+                    // table offset = slot * 256 + code byte: byte j of tw, byte 0 of `warp`, then zeros (bytes 1 of `warp`)
+                    const uint32_t o0 = __byte_perm(tw[wi], warp, 0x5540u), o1 = __byte_perm(tw[wi], warp, 0x5541u);
+                    const uint32_t o2 = __byte_perm(tw[wi], warp, 0x5542u), o3 = __byte_perm(tw[wi], warp, 0x5543u);
+                    step2<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, o0), lds_row(s_peq, o1), mul, m);
+                    step2<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, o2), lds_row(s_peq, o3), mul, m);
+                }
+                v = nxt;
+            }
+            if (rem) {
+                const uint32_t tw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if ((uint32_t)(wi * 4 + j) < rem) {
-                        const uint32_t off = (j == 0) ? (tw[wi] & 0xFFu)
-                                           : (j == 3) ? (tw[wi] >> 24)
-                                                      : __byte_perm(tw[wi], 0u, 0x4440u + j);
-                        step1<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, off), mul, m);
+                for (int wi = 0; wi < 4; wi++) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if ((uint32_t)(wi * 4 + j) < rem) {
+                            const uint32_t off = __byte_perm(tw[wi], warp, 0x5540u + j);
+                            step1<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, off), mul, m);
+                        }
                     }
                 }
             }
-        }
-        // hits of this read: [d<=0] + [d<=1] + [d<=2] per k-mer (:589-593); lanes past
-        // the last read of a partial tile hold padding and must not count (k <= 2
-        // matches the empty string)
-        if ((uint64_t)tile * kTileReads + lane >= n_reads) continue;
+            // hits of this read: [d<=0] + [d<=1] + [d<=2] per k-mer (:589-593); lanes past
+            // the last read of a partial tile hold padding and must not count (k <= 2
+            // matches the empty string)
+            if ((uint64_t)tile * kTileReads + lane >= n_reads) continue;
 #pragma unroll
-        for (int u = 0; u < UNITS; u++) {
-            const int w = u * NW + ACC0;
+            for (int u = 0; u < UNITS; u++) {
+                const int w = u * NW + ACC0;
 #pragma unroll
-            for (int f = 0; f < F; f++) {
-                const uint32_t sh = top_shift + f;
-                cnt[u * F + f] += ((a0[w] >> sh) & 1u) + ((a1[w] >> sh) & 1u) + ((a2[w] >> sh) & 1u);
+                for (int f = 0; f < F; f++) {
+                    const uint32_t sh = top_shift + f;
+                    cnt[u * F + f] += ((a0[w] >> sh) & 1u) + ((a1[w] >> sh) & 1u) + ((a2[w] >> sh) & 1u);
+                }
             }
         }
-    }
 
 #pragma unroll
-    for (int i = 0; i < UNITS * F; i++) {
-        const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, cnt[i]);
-        const uint32_t slot = g * (UNITS * F) + i; // == index of the k-mer; the last group may be padded
-        if (lane == 0 && total && slot < n_kmers) atomicAdd(&counts[slot], (unsigned long long)total);
+        for (int i = 0; i < UNITS * F; i++) {
+            const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, cnt[i]);
+            const uint32_t kslot = g * (UNITS * F) + i; // == index of the k-mer; the last group may be padded
+            if (lane == 0 && total && kslot < n_kmers) atomicAdd(&counts[kslot], (unsigned long long)total);
+        }
     }
 }
 
@@ -280,14 +302,17 @@ struct ScanRange {
 template <int NW, int F>
 static cudaError_t launch_variant(const Ctx &c, const ScanRange &r, unsigned long long *d_counts,
                                   uint32_t tiles_per_job) {
-    const uint32_t jobs = (r.n_tiles + tiles_per_job - 1) / tiles_per_job;
-    const uint64_t grid = (uint64_t)jobs * c.n_groups;
-    if (grid == 0 || grid > 0x7FFFFFFFull) return grid ? cudaErrorInvalidConfiguration : cudaSuccess;
+    const uint64_t jobs = (uint64_t)((r.n_tiles + tiles_per_job - 1) / tiles_per_job) * c.n_groups;
+    if (jobs == 0) return cudaSuccess;
+    if (jobs > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
     const uint32_t mul = 1u << F;
     uint32_t top = (uint32_t)(c.k - 1) * F;
     if (NW == 2) top -= 32; // relative to the high word
-    approx_scan_kernel<NW, F><<<(unsigned)grid, kScanWarps * 32, 0, c.stream>>>(
-        r.tiles, r.n_tiles, r.n_reads, c.chunks, c.max_len, c.d_peq, c.n_groups, tiles_per_job, mul, top, c.n_kmers, d_counts);
+    const uint64_t wave = (uint64_t)c.sm_count * kMinBlocks;
+    const unsigned grid = (unsigned)std::min<uint64_t>(wave, (jobs + kScanWarps - 1) / kScanWarps);
+    approx_scan_kernel<NW, F><<<grid, kScanWarps * 32, 0, c.stream>>>(
+        r.tiles, r.n_tiles, r.n_reads, c.chunks, c.max_len, c.d_peq, c.n_groups, tiles_per_job, (uint32_t)jobs, mul,
+        top, c.n_kmers, d_counts, c.d_job_counter);
     return cudaGetLastError();
 }
 
@@ -309,14 +334,14 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
 
     uint32_t tpj = (uint32_t)c.opt_tiles_per_job;
     if (tpj == 0) {
-        // aim for >= 16 waves of (SMs x resident CTAs) when the problem allows it,
-        // never less than one tile per warp
-        const uint64_t target = (uint64_t)c.sm_count * kMinBlocks * 16;
+        // a job is tiles_per_job tiles x one k-mer group for ONE warp.  Aim for >= 64 jobs per
+        // resident warp (tail <= 1/64 of the run) but keep jobs long enough (>= 2 tiles when
+        // possible) that the table load and the count flush stay below 1 % of a job.
+        const uint64_t warps = (uint64_t)c.sm_count * kMinBlocks * kScanWarps;
         const uint64_t work = (uint64_t)r.n_tiles * c.n_groups;
-        uint64_t t = work / (target ? target : 1);
-        t = (t / kScanWarps) * kScanWarps;
-        if (t < kScanWarps) t = kScanWarps;
-        if (t > 1024) t = 1024;
+        uint64_t t = work / (warps * 64);
+        if (t < 1) t = 1;
+        if (t > 16) t = 16;
         tpj = (uint32_t)t;
     }
     *launches = 1;

@@ -47,6 +47,15 @@ ALGO_OPS_PER_COLUMN = 16  # Myers/Hyyro column update, the figur
 L2_FLUSH_BYTES = 256 << 20
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -220,7 +229,7 @@ def run_reference(args, w):
         "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -309,8 +318,8 @@ def run_b200(args, w):
     # steps sits outside the event pairs), clocks sampled meanwhile
     gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
     sampler = ClockSampler(gpu_uuid if gpu_uuid.startswith("GPU-") else "GPU-" + gpu_uuid) if rank == 0 else None
-    if sampler is not None:
-        time.sleep(0.12)
+    time.sleep(0.12)  # let the sampler produce its first rows; every rank waits alike
+    barrier()         # ... and all ranks enter the timed region together
     launches[0] = 0
     step_events = []
     t_mark0 = time.perf_counter()
@@ -465,7 +474,7 @@ def run_b200(args, w):
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     for c in ctxs:
         c.close()
     if world > 1:
@@ -474,6 +483,12 @@ def run_b200(args, w):
 
 
 def main():
+    # stdout carries exactly one JSON line: park fd 1 on stderr while libraries (NCCL banner,
+    # torchrun notices) may print, and write the line to the saved descriptor at the end
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)

@@ -20,8 +20,10 @@ def run(c, n, L, k, q, variant=0, tpj=0, reps=5):
 if __name__ == "__main__":
     with ApproxCounter(0) as c:
         print(json.dumps(c.measure_int_peak()))
-        for args in [(10000, 100, 16, 500), (100000, 100, 16, 2000), (100000, 101, 16, 2000),
-                     (100000, 100, 16, 2000, 1), (200000, 150, 20, 2000), (200000, 150, 20, 2000, 1),
-                     (200000, 200, 32, 2000), (100000, 100, 10, 2000), (100000, 100, 16, 2000, 0, 8),
-                     (100000, 100, 16, 2000, 0, 64), (100000, 100, 16, 2000, 0, 512)]:
+        cases = [(10000, 100, 16, 500), (100000, 100, 16, 2000), (100000, 101, 16, 2000),
+                 (100000, 100, 16, 2000, 0, 1), (100000, 100, 16, 2000, 0, 2), (100000, 100, 16, 2000, 0, 4),
+                 (100000, 100, 16, 2000, 0, 8), (100000, 100, 16, 2000, 0, 32),
+                 (100000, 100, 16, 2000, 1), (200000, 150, 20, 2000), (200000, 150, 20, 2000, 1),
+                 (200000, 200, 32, 2000), (100000, 100, 10, 2000), (1000000, 150, 20, 5000, 0, 0, 2)]
+        for args in cases:
             print(json.dumps(run(c, *args)), flush=True)
