@@ -52,6 +52,7 @@ SYMBOLS = {
     "apc_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "apc_measure_int_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double)]),
+    "apc_microbench": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -171,6 +171,12 @@ class ApproxCounter:
         return {"lop3_ops_per_s": a.value, "imad_ops_per_s": b.value, "mixed_ops_per_s": c.value}
 
 
+    def microbench(self, name):
+        v = C.c_double()
+        self._check(self._lib.apc_microbench(self._h, name.encode(), C.byref(v)))
+        return v.value
+
+
 def device_count():
     n = _lib.load().apc_device_count()
     return max(0, n)

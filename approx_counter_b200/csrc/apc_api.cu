@@ -58,7 +58,8 @@ static int prepare_sample(Ctx *c, uint64_t n_reads, uint32_t max_len, uint64_t t
     c->total_bases = total_bases;
     c->n_tiles = (uint32_t)((n_reads + kTileReads - 1) / kTileReads);
     c->chunks = (max_len + kChunkBases - 1) / kChunkBases;
-    const size_t tiles_bytes = (size_t)c->n_tiles * c->chunks * kTileReads * sizeof(uint4);
+    // + one chunk of padding: the scan kernel always prefetches the next 512 bytes
+    const size_t tiles_bytes = ((size_t)c->n_tiles * c->chunks + 1) * kTileReads * sizeof(uint4);
     int st = grow(c, c->d_tiles, c->tiles_bytes, tiles_bytes);
     if (st) return st;
     const size_t lens_bytes = ((size_t)c->n_tiles * kTileReads + 1) * sizeof(uint32_t);
@@ -343,6 +344,11 @@ int apc_set_option(apc_ctx *c, const char *name, int64_t value) {
         c->opt_tiles_per_job = (int)value;
         return APC_OK;
     }
+    if (!std::strcmp(name, "scan_min_blocks")) {
+        if (value != 3 && value != 4) return apc::fail(c, APC_ERR_INVALID, "scan_min_blocks must be 3 or 4");
+        c->opt_min_blocks = (int)value;
+        return APC_OK;
+    }
     if (!std::strcmp(name, "scan_first_read")) {
         if (value < 0 || value % apc::kTileReads) return apc::fail(c, APC_ERR_INVALID, "scan_first_read must be a multiple of 32");
         c->opt_first_read = (uint64_t)value;
@@ -359,6 +365,14 @@ int apc_measure_int_peak(apc_ctx *c, double *lop3, double *imad, double *mixed) 
     int st = apc::bind(c);
     if (st) return st;
     APC_CUDA(c, apc::measure_int_peak(*c, lop3, imad, mixed));
+    return APC_OK;
+}
+
+int apc_microbench(apc_ctx *c, const char *name, double *value) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (!name || !value) return apc::fail(c, APC_ERR_INVALID, "NULL argument");
+    APC_CUDA(c, apc::microbench(*c, name, value));
     return APC_OK;
 }
 

@@ -95,6 +95,7 @@ struct Ctx {
     // options
     int opt_variant = 0;
     int opt_tiles_per_job = 0;
+    int opt_min_blocks = 3;       // resident CTAs per SM the scan kernel is compiled for (3: 80 regs, 4: 64 regs)
     uint64_t opt_first_read = 0;  // scan only reads [first, first+n) of the resident sample
     int64_t opt_n_reads = -1;     // -1 = to the end
 
@@ -139,6 +140,7 @@ void free_exact_scratch(Ctx *c);
 
 // peak_kernels.cu
 cudaError_t measure_int_peak(const Ctx &c, double *lop3, double *imad, double *mixed);
+cudaError_t microbench(const Ctx &c, const char *name, double *value);
 
 } // namespace apc
 

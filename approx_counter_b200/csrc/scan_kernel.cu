@@ -13,7 +13,9 @@
 // read so far with <= e edits".  Per text column:
 //     R0' = ((R0 << 1) | 1) & Eq
 //     Re' = ((Re << 1) & Eq) | R(e-1) | (R(e-1) << 1) | (R(e-1)' << 1) | 1
-// and a read is flagged at level e when bit k-1 of Re was ever set.
+// and a read is flagged at level e when bit k-1 of Re was ever set.  The
+// shifted levels are carried between columns (scan_core.cuh), so a column costs
+// three shifts, not five.
 //
 // B200 mapping (integer-pipe bound, no tensor cores, text stays in L2/HBM):
 //  * lane = read.  A warp walks one 32-read tile; its 128-bit tile loads are
@@ -25,8 +27,7 @@
 //      k<=10: 3 per 32-bit word, k<=16: 2 per word, k<=21: 3 per 64-bit pair.
 //  * the shifts are issued as IMAD (FMA pipe) by passing 2^F as a runtime
 //    operand; the boolean algebra is LOP3 (ALU pipe).  Per unit and column
-//    that is 5 IMAD + 5 LOP3 + 1.5 LOP3 of hit accumulation — both integer
-//    pipes stay busy instead of only the ALU.
+//    that is 3 IMAD + 5 LOP3 + 1.5 LOP3 of hit accumulation.
 //  * Eq comes from a 5-row x 16-byte match table in shared memory, one
 //    LDS.128 per column per thread (4 state words); the text byte already is
 //    the row offset, so no address arithmetic is spent on it.
@@ -35,10 +36,10 @@
 #include <algorithm>
 
 #include "apc_internal.h"
+#include "scan_core.cuh"
 
 namespace apc {
 
-constexpr int kMinBlocks = 3;
 
 ScanVariant pick_variant(int k, int forced) {
     ScanVariant v{1, 1};
@@ -75,109 +76,6 @@ void build_peq_tables(const uint64_t *kmers, uint32_t n_kmers, int k, ScanVarian
     }
 }
 
-// ---- text columns for the four state words of a thread --------------------------
-// core() advances the automaton by one column and returns the new levels in
-// n0/n1/n2 (also stored to r0/r1/r2).  Hit accumulation is separate so that
-// two columns share one 3-input OR per level (acc |= nA | nB = one LOP3).
-// Boolean steps are pinned to one LOP3 each (inline PTX is opaque to nvcc's
-// re-association, which otherwise regroups the OR chains into 8 LOP3 per column
-// instead of 6.5).  LUT = f(0xF0, 0xCC, 0xAA).
-template <int LUT>
-__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
-    return d;
-}
-__device__ __forceinline__ uint32_t and2(uint32_t a, uint32_t b) { return lop3<0xC0>(a, b, 0u); }       // a & b
-__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) { return lop3<0xEA>(a, b, c); } // (a & b) | c
-__device__ __forceinline__ uint32_t or3(uint32_t a, uint32_t b, uint32_t c) { return lop3<0xFE>(a, b, c); }    // a | b | c
-
-template <int NW>
-struct Column;
-
-template <>
-struct Column<1> {
-    // one unit per word
-    static __device__ __forceinline__ void core(uint32_t (&r0)[4], uint32_t (&r1)[4], uint32_t (&r2)[4],
-                                                const uint4 eq4, const uint32_t mul, const uint32_t m) {
-        const uint32_t eq[4] = {eq4.x, eq4.y, eq4.z, eq4.w};
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t a = r0[u] * mul + m;  // (R0 << F) | 1s
-            const uint32_t n0 = and2(a, eq[u]);
-            const uint32_t s1 = r1[u] * mul + m; // (R1 << F) | 1s
-            const uint32_t d0 = n0 * mul;        // R0' << F
-            const uint32_t n1 = or3(and_or(s1, eq[u], r0[u]), a, d0);
-            const uint32_t s2 = r2[u] * mul;     // R2 << F
-            const uint32_t d1 = n1 * mul;        // R1' << F
-            const uint32_t n2 = or3(and_or(s2, eq[u], r1[u]), s1, d1);
-            r0[u] = n0; r1[u] = n1; r2[u] = n2;
-        }
-    }
-};
-
-template <>
-struct Column<2> {
-    // two units of 64 bits: words (0,1) and (2,3) as (lo,hi)
-    static __device__ __forceinline__ void shl(uint32_t lo, uint32_t hi, uint32_t mul, uint32_t add,
-                                               uint32_t &olo, uint32_t &ohi) {
-        const unsigned long long t = (unsigned long long)lo * mul + add; // IMAD.WIDE
-        olo = (uint32_t)t;
-        ohi = hi * mul + (uint32_t)(t >> 32);
-    }
-    static __device__ __forceinline__ void core(uint32_t (&r0)[4], uint32_t (&r1)[4], uint32_t (&r2)[4],
-                                                const uint4 eq4, const uint32_t mul, const uint32_t m) {
-        const uint32_t eq[4] = {eq4.x, eq4.y, eq4.z, eq4.w};
-#pragma unroll
-        for (int u = 0; u < 4; u += 2) {
-            uint32_t al, ah, s1l, s1h, d0l, d0h, s2l, s2h, d1l, d1h;
-            shl(r0[u], r0[u + 1], mul, m, al, ah);
-            const uint32_t n0l = and2(al, eq[u]), n0h = and2(ah, eq[u + 1]);
-            shl(r1[u], r1[u + 1], mul, m, s1l, s1h);
-            shl(n0l, n0h, mul, 0u, d0l, d0h);
-            const uint32_t n1l = or3(and_or(s1l, eq[u], r0[u]), al, d0l);
-            const uint32_t n1h = or3(and_or(s1h, eq[u + 1], r0[u + 1]), ah, d0h);
-            shl(r2[u], r2[u + 1], mul, 0u, s2l, s2h);
-            shl(n1l, n1h, mul, 0u, d1l, d1h);
-            const uint32_t n2l = or3(and_or(s2l, eq[u], r1[u]), s1l, d1l);
-            const uint32_t n2h = or3(and_or(s2h, eq[u + 1], r1[u + 1]), s1h, d1h);
-            r0[u] = n0l; r0[u + 1] = n0h;
-            r1[u] = n1l; r1[u + 1] = n1h;
-            r2[u] = n2l; r2[u + 1] = n2h;
-        }
-    }
-};
-
-// One column, accumulate immediately (tail columns).
-template <int NW>
-__device__ __forceinline__ void step1(uint32_t (&r0)[4], uint32_t (&r1)[4], uint32_t (&r2)[4],
-                                      uint32_t (&a0)[4], uint32_t (&a1)[4], uint32_t (&a2)[4],
-                                      const uint4 eq, const uint32_t mul, const uint32_t m) {
-    Column<NW>::core(r0, r1, r2, eq, mul, m);
-#pragma unroll
-    for (int w = NW - 1; w < 4; w += NW) { // row k-1 lives in the last word of a unit
-        a0[w] |= r0[w]; a1[w] |= r1[w]; a2[w] |= r2[w];
-    }
-}
-
-// Two columns, one 3-input OR per level and word.
-template <int NW>
-__device__ __forceinline__ void step2(uint32_t (&r0)[4], uint32_t (&r1)[4], uint32_t (&r2)[4],
-                                      uint32_t (&a0)[4], uint32_t (&a1)[4], uint32_t (&a2)[4],
-                                      const uint4 eqa, const uint4 eqb, const uint32_t mul, const uint32_t m) {
-    Column<NW>::core(r0, r1, r2, eqa, mul, m);
-    uint32_t p0[4], p1[4], p2[4];
-#pragma unroll
-    for (int w = 0; w < 4; w++) { p0[w] = r0[w]; p1[w] = r1[w]; p2[w] = r2[w]; }
-    Column<NW>::core(r0, r1, r2, eqb, mul, m);
-#pragma unroll
-    for (int w = NW - 1; w < 4; w += NW) {
-        a0[w] = or3(a0[w], p0[w], r0[w]);
-        a1[w] = or3(a1[w], p1[w], r1[w]);
-        a2[w] = or3(a2[w], p2[w], r2[w]);
-    }
-}
-
 __device__ __forceinline__ uint4 lds_row(const uint32_t *table, const uint32_t off) {
     return *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(table) + off);
 }
@@ -192,9 +90,15 @@ __device__ __forceinline__ uint4 ldg_tile(const uint4 *p) { return __ldg(p); }
 // its current group; the slot index is merged into the table offset by the same PRMT that
 // extracts the text byte, so a column still costs one PRMT + one LDS.128 per thread.
 constexpr int kSlotBytes = 256;
+constexpr uint32_t kMaxTilesPerJob = 64; // 3 hits x 64 tiles < 256: the packed byte counters cannot overflow
 
-template <int NW, int F>
-__global__ void __launch_bounds__(kScanWarps * 32, kMinBlocks)
+template <int F>
+__device__ __forceinline__ constexpr uint32_t kFieldMask() {
+    return F == 1 ? 0x000001u : F == 2 ? 0x000101u : 0x010101u;
+}
+
+template <int NW, int F, int MB>
+__global__ void __launch_bounds__(kScanWarps * 32, MB)
 approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, const uint64_t n_reads,
                    const uint32_t chunks, const uint32_t read_len, const uint32_t *__restrict__ peq,
                    const uint32_t n_groups, const uint32_t tiles_per_job, const uint32_t n_jobs,
@@ -227,68 +131,81 @@ approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, cons
         const uint32_t tile_begin = tb * tiles_per_job;
         const uint32_t tile_end = min(n_tiles, tile_begin + tiles_per_job);
 
-        uint32_t cnt[UNITS * F];
+        // per unit: F byte-wide hit counters packed in one register (<= 3 hits per read,
+        // <= kMaxTilesPerJob tiles per job, so a byte cannot overflow)
+        uint32_t cntw[UNITS];
 #pragma unroll
-        for (int i = 0; i < UNITS * F; i++) cnt[i] = 0;
+        for (int u = 0; u < UNITS; u++) cntw[u] = 0;
 
+        // Chunks of consecutive tiles are contiguous in memory, so "the next 512 bytes" is
+        // always the right prefetch — also across a tile boundary (the buffer is padded by
+        // one chunk so the very last prefetch stays in bounds).
+        const uint4 *p = tiles + (size_t)tile_begin * chunks * kTileReads + lane;
+        uint4 v = ldg_tile(p);
         for (uint32_t tile = tile_begin; tile < tile_end; tile++) {
-            uint32_t r0[4], r1[4], r2[4], a0[4], a1[4], a2[4];
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-                const bool low = (NW == 1) || ((w & 1) == 0);
-                r0[w] = 0;
-                r1[w] = low ? m : 0;            // prefix 1 by one deletion
-                r2[w] = low ? (m * mul + m) : 0; // prefixes 1..2 by deletions
-                a0[w] = r0[w]; a1[w] = r1[w]; a2[w] = r2[w];
-            }
-            const uint4 *p = tiles + (size_t)tile * chunks * kTileReads + lane;
-            uint4 v = ldg_tile(p);
+            ScanState st;
+            Column<NW>::init(st, mul, m);
             for (uint32_t ch = 0; ch < full; ch++) {
-                const uint4 nxt = (ch + 1 < chunks) ? ldg_tile(p + (size_t)(ch + 1) * kTileReads) : v;
+                p += kTileReads;
+                const uint4 nxt = ldg_tile(p);
                 const uint32_t tw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int wi = 0; wi < 4; wi++) {
                     // table offset = slot * 256 + code byte: byte j of tw, byte 0 of `warp`, then zeros (bytes 1 of `warp`)
                     const uint32_t o0 = __byte_perm(tw[wi], warp, 0x5540u), o1 = __byte_perm(tw[wi], warp, 0x5541u);
                     const uint32_t o2 = __byte_perm(tw[wi], warp, 0x5542u), o3 = __byte_perm(tw[wi], warp, 0x5543u);
-                    step2<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, o0), lds_row(s_peq, o1), mul, m);
-                    step2<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, o2), lds_row(s_peq, o3), mul, m);
+                    step2<NW>(st, lds_row(s_peq, o0), lds_row(s_peq, o1), mul, m);
+                    step2<NW>(st, lds_row(s_peq, o2), lds_row(s_peq, o3), mul, m);
                 }
                 v = nxt;
             }
             if (rem) {
+                // The last, partial chunk also goes through the two-column step: an odd
+                // length is rounded up with one padding column.  Padding is coded N (matches
+                // nothing), and a text character that matches nothing can never lower the
+                // minimum edit distance (aligning to it costs 1, like skipping the k-mer
+                // character instead), so the extra column cannot create a hit.
+                p += kTileReads;
+                const uint4 nxt = ldg_tile(p);
                 const uint32_t tw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int wi = 0; wi < 4; wi++) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if ((uint32_t)(wi * 4 + j) < rem) {
-                            const uint32_t off = __byte_perm(tw[wi], warp, 0x5540u + j);
-                            step1<NW>(r0, r1, r2, a0, a1, a2, lds_row(s_peq, off), mul, m);
-                        }
+                    if ((uint32_t)(wi * 4) < rem) { // warp-uniform
+                        const uint32_t o0 = __byte_perm(tw[wi], warp, 0x5540u), o1 = __byte_perm(tw[wi], warp, 0x5541u);
+                        step2<NW>(st, lds_row(s_peq, o0), lds_row(s_peq, o1), mul, m);
+                    }
+                    if ((uint32_t)(wi * 4 + 2) < rem) {
+                        const uint32_t o2 = __byte_perm(tw[wi], warp, 0x5542u), o3 = __byte_perm(tw[wi], warp, 0x5543u);
+                        step2<NW>(st, lds_row(s_peq, o2), lds_row(s_peq, o3), mul, m);
                     }
                 }
+                v = nxt;
             }
-            // hits of this read: [d<=0] + [d<=1] + [d<=2] per k-mer (:589-593); lanes past
-            // the last read of a partial tile hold padding and must not count (k <= 2
-            // matches the empty string)
-            if ((uint64_t)tile * kTileReads + lane >= n_reads) continue;
+            // hits of this read: [d<=0] + [d<=1] + [d<=2] per k-mer (:589-593).  The levels are
+            // nested (a0 ⊆ a1 ⊆ a2), so the sum is the 2-bit number (a1, a0^a1^a2) per k-mer.
+            // Lanes past the last read of a partial tile hold padding and must not count
+            // (k <= 2 matches the empty string).
+            const bool valid = (uint64_t)tile * kTileReads + lane < n_reads;
 #pragma unroll
             for (int u = 0; u < UNITS; u++) {
                 const int w = u * NW + ACC0;
-#pragma unroll
-                for (int f = 0; f < F; f++) {
-                    const uint32_t sh = top_shift + f;
-                    cnt[u * F + f] += ((a0[w] >> sh) & 1u) + ((a1[w] >> sh) & 1u) + ((a2[w] >> sh) & 1u);
-                }
+                // rows past k-1 may hold junk at levels 1 and 2: keep the F bits of row k-1 only
+                const uint32_t lo = ((st.a0[w] ^ st.a1[w] ^ st.a2[w]) >> top_shift) & ((1u << F) - 1u);
+                const uint32_t hi = (st.a1[w] >> top_shift) & ((1u << F) - 1u);
+                // spread field f (bit f) to byte f: x * (1 + 2^7 + 2^14) & 0x010101
+                const uint32_t slo = (lo * 0x4081u) & kFieldMask<F>(), shi = (hi * 0x4081u) & kFieldMask<F>();
+                if (valid) cntw[u] += slo + 2u * shi;
             }
         }
 
 #pragma unroll
-        for (int i = 0; i < UNITS * F; i++) {
-            const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, cnt[i]);
-            const uint32_t kslot = g * (UNITS * F) + i; // == index of the k-mer; the last group may be padded
-            if (lane == 0 && total && kslot < n_kmers) atomicAdd(&counts[kslot], (unsigned long long)total);
+        for (int u = 0; u < UNITS; u++) {
+#pragma unroll
+            for (int f = 0; f < F; f++) {
+                const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, (cntw[u] >> (8 * f)) & 0xFFu);
+                const uint32_t kslot = g * (UNITS * F) + u * F + f; // == index of the k-mer; the last group may be padded
+                if (lane == 0 && total && kslot < n_kmers) atomicAdd(&counts[kslot], (unsigned long long)total);
+            }
         }
     }
 }
@@ -299,7 +216,7 @@ struct ScanRange {
     uint64_t n_reads;   // reads in the range (relative to its first tile)
 };
 
-template <int NW, int F>
+template <int NW, int F, int MB>
 static cudaError_t launch_variant(const Ctx &c, const ScanRange &r, unsigned long long *d_counts,
                                   uint32_t tiles_per_job) {
     const uint64_t jobs = (uint64_t)((r.n_tiles + tiles_per_job - 1) / tiles_per_job) * c.n_groups;
@@ -308,9 +225,9 @@ static cudaError_t launch_variant(const Ctx &c, const ScanRange &r, unsigned lon
     const uint32_t mul = 1u << F;
     uint32_t top = (uint32_t)(c.k - 1) * F;
     if (NW == 2) top -= 32; // relative to the high word
-    const uint64_t wave = (uint64_t)c.sm_count * kMinBlocks;
+    const uint64_t wave = (uint64_t)c.sm_count * MB;
     const unsigned grid = (unsigned)std::min<uint64_t>(wave, (jobs + kScanWarps - 1) / kScanWarps);
-    approx_scan_kernel<NW, F><<<grid, kScanWarps * 32, 0, c.stream>>>(
+    approx_scan_kernel<NW, F, MB><<<grid, kScanWarps * 32, 0, c.stream>>>(
         r.tiles, r.n_tiles, r.n_reads, c.chunks, c.max_len, c.d_peq, c.n_groups, tiles_per_job, (uint32_t)jobs, mul,
         top, c.n_kmers, d_counts, c.d_job_counter);
     return cudaGetLastError();
@@ -337,18 +254,23 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
         // a job is tiles_per_job tiles x one k-mer group for ONE warp.  Aim for >= 64 jobs per
         // resident warp (tail <= 1/64 of the run) but keep jobs long enough (>= 2 tiles when
         // possible) that the table load and the count flush stay below 1 % of a job.
-        const uint64_t warps = (uint64_t)c.sm_count * kMinBlocks * kScanWarps;
+        const uint64_t warps = (uint64_t)c.sm_count * (c.opt_min_blocks == 4 ? 4 : 3) * kScanWarps;
         const uint64_t work = (uint64_t)r.n_tiles * c.n_groups;
         uint64_t t = work / (warps * 64);
         if (t < 1) t = 1;
         if (t > 16) t = 16;
         tpj = (uint32_t)t;
     }
+    if (tpj > kMaxTilesPerJob) tpj = kMaxTilesPerJob;
     *launches = 1;
-    if (c.variant.nw == 1 && c.variant.f == 1) return launch_variant<1, 1>(c, r, d_counts, tpj);
-    if (c.variant.nw == 1 && c.variant.f == 2) return launch_variant<1, 2>(c, r, d_counts, tpj);
-    if (c.variant.nw == 1 && c.variant.f == 3) return launch_variant<1, 3>(c, r, d_counts, tpj);
-    if (c.variant.nw == 2 && c.variant.f == 3) return launch_variant<2, 3>(c, r, d_counts, tpj);
+    const bool mb4 = c.opt_min_blocks == 4;
+    if (c.variant.nw == 1 && c.variant.f == 1)
+        return mb4 ? launch_variant<1, 1, 4>(c, r, d_counts, tpj) : launch_variant<1, 1, 3>(c, r, d_counts, tpj);
+    if (c.variant.nw == 1 && c.variant.f == 2)
+        return mb4 ? launch_variant<1, 2, 4>(c, r, d_counts, tpj) : launch_variant<1, 2, 3>(c, r, d_counts, tpj);
+    if (c.variant.nw == 1 && c.variant.f == 3) return launch_variant<1, 3, 3>(c, r, d_counts, tpj);
+    if (c.variant.nw == 2 && c.variant.f == 3)
+        return mb4 ? launch_variant<2, 3, 4>(c, r, d_counts, tpj) : launch_variant<2, 3, 3>(c, r, d_counts, tpj);
     return cudaErrorInvalidValue;
 }
 

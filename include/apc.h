@@ -144,6 +144,13 @@ int apc_set_option(apc_ctx *ctx, const char *name, int64_t value);
 int apc_measure_int_peak(apc_ctx *ctx, double *lop3_ops_per_s,
                          double *imad_ops_per_s, double *mixed_ops_per_s);
 
+/* Single microbenchmarks behind the figures above and the tuning notes in
+ * "lop3", "imad", "mixed", "imad_hi", "imad_wide" return lane-ops
+ * per second; "core_<sets>_<threads>_<ctas>" (see peak_kernels.cu) run
+ * the scan kernel's column update from registers (no loads) and return
+ * unit-columns per second. */
+int apc_microbench(apc_ctx *ctx, const char *name, double *value);
+
 #ifdef __cplusplus
 }
 #endif
