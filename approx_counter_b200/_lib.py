@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libapc.so")
+# APC_LIB_PATH: development override used by tools/ to A/B differently compiled builds
+LIB_PATH = os.environ.get("APC_LIB_PATH") or os.path.join(_HERE, "csrc", "libapc.so")
 
 APC_OK = 0
 ERRORS = {

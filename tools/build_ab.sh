@@ -1,0 +1,14 @@
+#!/bin/bash
+# Build A/B variants of libapc.so with extra -D flags:  tools/build_ab.sh name "-DFOO=1" ...
+# Result: approx_counter_b200/csrc/ab/libapc_<name>.so (git-ignored, travels with gpurun).
+set -e
+name=$1; shift
+cd "$(dirname "$0")/../approx_counter_b200/csrc"
+mkdir -p ab/$name/host
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+for f in apc_api scan_kernel sample_kernels exact_kernels peak_kernels; do
+  nvcc $ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include -I. -Ihost "$@" -c $f.cu -o ab/$name/$f.o &
+done
+wait
+nvcc $ARCH -shared -o ab/libapc_$name.so ab/$name/*.o host/host_util.o host/cli.o host/host_abi.o -cudart static -lgomp
+echo built ab/libapc_$name.so
