@@ -38,6 +38,7 @@ SYMBOLS = {
     "apc_set_stream": (C.c_int, [_vp, _vp]),
     "apc_sync": (C.c_int, [_vp]),
     "apc_upload_sample": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32]),
+    "apc_upload_sample_async": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32]),
     "apc_upload_sample_ragged": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
     "apc_sample_info": (C.c_int, [_vp, _u64p, C.POINTER(C.c_uint32), _u64p]),
     "apc_exact_topn": (C.c_int, [_vp, C.c_uint8, C.c_float, C.c_uint64, _vp, C.c_uint64,
@@ -45,6 +46,7 @@ SYMBOLS = {
     "apc_exact_solid": (C.c_int, [_vp, C.c_uint8, C.c_float, C.c_uint64, _vp, C.c_uint64,
                                   _vp, _vp, C.c_uint64, _u64p, _u64p, _u64p]),
     "apc_approx_count": (C.c_int, [_vp, C.c_uint8, _vp, C.c_uint32, _vp]),
+    "apc_approx_count_async": (C.c_int, [_vp, C.c_uint8, _vp, C.c_uint32, _vp]),
     "apc_set_queries": (C.c_int, [_vp, C.c_uint8, _vp, C.c_uint32]),
     "apc_scan": (C.c_int, [_vp, _vp]),
     "apc_get_counts": (C.c_int, [_vp, _vp]),

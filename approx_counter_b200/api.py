@@ -91,6 +91,11 @@ class ApproxCounter:
         """Same, from a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
         self._check(self._lib.apc_upload_sample(self._h, C.c_void_p(int(host_ptr)), int(n_reads), int(read_len)))
 
+    def upload_sample_ptr_async(self, host_ptr, n_reads, read_len):
+        """Enqueue only; the (page-locked) buffer must stay valid until sync()."""
+        self._check(self._lib.apc_upload_sample_async(self._h, C.c_void_p(int(host_ptr)), int(n_reads),
+                                                      int(read_len)))
+
     def sample_info(self):
         n, ml, tb = C.c_uint64(), C.c_uint32(), C.c_uint64()
         self._check(self._lib.apc_sample_info(self._h, C.byref(n), C.byref(ml), C.byref(tb)))
@@ -136,6 +141,11 @@ class ApproxCounter:
     def errorCount_ptr(self, kmers_ptr, n_kmers, k, counts_ptr):
         self._check(self._lib.apc_approx_count(self._h, int(k), C.c_void_p(int(kmers_ptr)), int(n_kmers),
                                                C.c_void_p(int(counts_ptr))))
+
+    def errorCount_ptr_async(self, kmers_ptr, n_kmers, k, counts_ptr):
+        """Enqueue only; counts are valid after sync()."""
+        self._check(self._lib.apc_approx_count_async(self._h, int(k), C.c_void_p(int(kmers_ptr)), int(n_kmers),
+                                                     C.c_void_p(int(counts_ptr))))
 
     def set_queries(self, kmers, k):
         km = _as_kmers(kmers)

@@ -1,6 +1,7 @@
 // apc_api.cu — the C ABI of libapc (include/apc.h): context, sample upload,
 // query upload, scan, result read-back, timing.  Plain pointers and sizes
 // only; every CUDA failure becomes a status code plus apc_last_error text.
+#include <algorithm>
 #include <cstring>
 #include <new>
 
@@ -111,7 +112,8 @@ int apc_create(int device, apc_ctx **out) {
     c->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_table, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_job_counter, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->d_job_counter, 0, sizeof(unsigned int));
@@ -139,6 +141,7 @@ void apc_destroy(apc_ctx *c) {
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
+    if (c->ev_table) cudaEventDestroy(c->ev_table);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -158,7 +161,7 @@ int apc_sync(apc_ctx *c) {
     return APC_OK;
 }
 
-int apc_upload_sample(apc_ctx *c, const uint8_t *bases, uint64_t n_reads, uint32_t read_len) {
+int apc_upload_sample_async(apc_ctx *c, const uint8_t *bases, uint64_t n_reads, uint32_t read_len) {
     int st = apc::bind(c);
     if (st) return st;
     if (!bases && n_reads * read_len) return apc::fail(c, APC_ERR_INVALID, "bases is NULL");
@@ -171,6 +174,13 @@ int apc_upload_sample(apc_ctx *c, const uint8_t *bases, uint64_t n_reads, uint32
     APC_CUDA(c, apc::launch_build_tiles_uniform(c->d_stage, n_reads, read_len, c->chunks, c->n_tiles,
                                                 c->d_tiles, c->d_lens, c->stream));
     APC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    c->timing.upload_ms = -1.f; // resolved lazily by apc_last_timing
+    return APC_OK;
+}
+
+int apc_upload_sample(apc_ctx *c, const uint8_t *bases, uint64_t n_reads, uint32_t read_len) {
+    int st = apc_upload_sample_async(c, bases, n_reads, read_len);
+    if (st) return st;
     APC_CUDA(c, cudaStreamSynchronize(c->stream)); // caller may free `bases` on return
     c->timing.upload_ms = apc::elapsed(c->ev[0], c->ev[1]);
     return APC_OK;
@@ -270,15 +280,32 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
     c->k = k;
     c->n_kmers = n_kmers;
     c->variant = apc::pick_variant(k, c->opt_variant);
-    std::vector<uint32_t> table;
-    apc::build_peq_tables(kmers, n_kmers, k, c->variant, table, c->n_groups);
-    if ((st = apc::grow(c, c->d_peq, c->peq_cap, table.size() * sizeof(uint32_t)))) return st;
-    const size_t slots = (size_t)c->n_groups * c->variant.queries_per_group();
+    // the match tables are built in a context-owned pinned buffer so that the H2D copy is
+    // truly asynchronous; the buffer is only rewritten once its previous copy has completed
+    const uint32_t qg = c->variant.queries_per_group();
+    const size_t table_words = (size_t)((n_kmers + qg - 1) / qg) * apc::kPeqRows * apc::kWordsPerThread;
+    if (c->table_copy_pending) {
+        APC_CUDA(c, cudaEventSynchronize(c->ev_table));
+        c->table_copy_pending = false;
+    }
+    if (table_words * sizeof(uint32_t) > c->pinned_cap) {
+        if (c->h_pinned) APC_CUDA(c, cudaFreeHost(c->h_pinned));
+        c->h_pinned = nullptr;
+        c->pinned_cap = 0;
+        const size_t cap = std::max<size_t>(table_words * sizeof(uint32_t) * 2, 1 << 16);
+        cudaError_t e = cudaMallocHost(&c->h_pinned, cap);
+        if (e != cudaSuccess) return apc::fail(c, APC_ERR_NOMEM, "cudaMallocHost", e);
+        c->pinned_cap = cap;
+    }
+    apc::build_peq_tables(kmers, n_kmers, k, c->variant, (uint32_t *)c->h_pinned, c->n_groups);
+    if ((st = apc::grow(c, c->d_peq, c->peq_cap, table_words * sizeof(uint32_t)))) return st;
+    const size_t slots = (size_t)c->n_groups * qg;
     if ((st = apc::grow(c, c->d_counts, c->counts_cap, slots * sizeof(unsigned long long)))) return st;
-    if (!table.empty()) {
-        APC_CUDA(c, cudaMemcpyAsync(c->d_peq, table.data(), table.size() * sizeof(uint32_t),
-                                    cudaMemcpyHostToDevice, c->stream));
-        APC_CUDA(c, cudaStreamSynchronize(c->stream)); // table is a local
+    if (table_words) {
+        APC_CUDA(c, cudaMemcpyAsync(c->d_peq, c->h_pinned, table_words * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                    c->stream));
+        APC_CUDA(c, cudaEventRecord(c->ev_table, c->stream));
+        c->table_copy_pending = true;
     }
     return APC_OK;
 }
@@ -310,16 +337,27 @@ int apc_get_counts(apc_ctx *c, uint64_t *counts_out) {
 
 uint64_t *apc_counts_device_ptr(apc_ctx *c) { return c ? (uint64_t *)c->d_counts : nullptr; }
 
-int apc_approx_count(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kmers, uint64_t *counts_out) {
+int apc_approx_count_async(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kmers, uint64_t *counts_out) {
     int st = apc::bind(c);
     if (st) return st;
     if (!c->has_sample) return apc::fail(c, APC_ERR_NO_SAMPLE, "apc_approx_count: no sample uploaded");
-    APC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if (!counts_out && n_kmers) return apc::fail(c, APC_ERR_INVALID, "counts_out is NULL");
+    APC_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
     if ((st = apc_set_queries(c, k, kmers, n_kmers))) return st;
     if ((st = apc_scan(c, nullptr))) return st;
-    if ((st = apc_get_counts(c, counts_out))) return st;
-    APC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-    c->timing.total_ms = apc::elapsed(c->ev[0], c->ev[1]);
+    if (n_kmers)
+        APC_CUDA(c, cudaMemcpyAsync(counts_out, c->d_counts, (size_t)n_kmers * sizeof(uint64_t),
+                                    cudaMemcpyDeviceToHost, c->stream));
+    APC_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    c->timing.total_ms = -1.f;
+    return APC_OK;
+}
+
+int apc_approx_count(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kmers, uint64_t *counts_out) {
+    int st = apc_approx_count_async(c, k, kmers, n_kmers, counts_out);
+    if (st) return st;
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->timing.total_ms = apc::elapsed(c->ev[4], c->ev[5]);
     return APC_OK;
 }
 
@@ -327,6 +365,8 @@ int apc_last_timing(const apc_ctx *cc, apc_timing *out) {
     apc_ctx *c = const_cast<apc_ctx *>(cc);
     if (!c || !out) return APC_ERR_INVALID;
     if (c->timing.scan_ms < 0.f) c->timing.scan_ms = apc::elapsed(c->ev[2], c->ev[3]);
+    if (c->timing.upload_ms < 0.f) c->timing.upload_ms = apc::elapsed(c->ev[0], c->ev[1]);
+    if (c->timing.total_ms < 0.f) c->timing.total_ms = apc::elapsed(c->ev[4], c->ev[5]);
     *out = c->timing;
     return APC_OK;
 }

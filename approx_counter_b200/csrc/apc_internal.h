@@ -57,7 +57,9 @@ struct Ctx {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // upload 0-1, scan 2-3, approx 4-5
+    cudaEvent_t ev_table = nullptr; // completion of the last match-table copy out of h_pinned
+    bool table_copy_pending = false;
     std::string err;
 
     // sample
@@ -127,8 +129,8 @@ cudaError_t launch_build_tiles_ragged(const uint8_t *d_ascii, const uint64_t *d_
 
 // scan_kernel.cu
 ScanVariant pick_variant(int k, int forced);
-void build_peq_tables(const uint64_t *kmers, uint32_t n_kmers, int k, ScanVariant v,
-                      std::vector<uint32_t> &table, uint32_t &n_groups);
+void build_peq_tables(const uint64_t *kmers, uint32_t n_kmers, int k, ScanVariant v, uint32_t *table,
+                      uint32_t &n_groups);
 cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *launches);
 
 // exact_kernels.cu

@@ -60,14 +60,14 @@ ScanVariant pick_variant(int k, int forced) {
 // thread word w.  k-mer q sits in group q / QG, unit (q % QG) / F, field
 // (q % QG) % F; row i (i-th base of the k-mer, :70-78 order) is bit i*F+f of
 // the unit.
-void build_peq_tables(const uint64_t *kmers, uint32_t n_kmers, int k, ScanVariant v,
-                      std::vector<uint32_t> &table, uint32_t &n_groups) {
+void build_peq_tables(const uint64_t *kmers, uint32_t n_kmers, int k, ScanVariant v, uint32_t *table,
+                      uint32_t &n_groups) {
     const uint32_t qg = v.queries_per_group();
     n_groups = (n_kmers + qg - 1) / qg;
-    table.assign((size_t)n_groups * kPeqRows * kWordsPerThread, 0u);
+    std::fill(table, table + (size_t)n_groups * kPeqRows * kWordsPerThread, 0u);
     for (uint32_t q = 0; q < n_kmers; q++) {
         const uint32_t g = q / qg, r = q % qg, u = r / v.f, f = r % v.f;
-        uint32_t *t = table.data() + (size_t)g * kPeqRows * kWordsPerThread;
+        uint32_t *t = table + (size_t)g * kPeqRows * kWordsPerThread;
         for (int i = 0; i < k; i++) {
             const uint32_t c = (kmers[q] >> (2 * (k - 1 - i))) & 3;
             const uint32_t bit = i * v.f + f;

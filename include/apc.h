@@ -79,6 +79,10 @@ int apc_sync(apc_ctx *ctx);
  * ends, :463/:466).  Letters other than ACGTacgt are N (Dna5, :38). */
 int apc_upload_sample(apc_ctx *ctx, const uint8_t *bases, uint64_t n_reads,
                       uint32_t read_len);
+/* Same, without the final synchronisation: `bases` must stay valid (and, to
+ * overlap with other work, be page-locked) until apc_sync returns. */
+int apc_upload_sample_async(apc_ctx *ctx, const uint8_t *bases, uint64_t n_reads,
+                            uint32_t read_len);
 /* Ragged form: read r is bases[offsets[r] .. offsets[r+1]). */
 int apc_upload_sample_ragged(apc_ctx *ctx, const uint8_t *bases,
                              const uint64_t *offsets, uint64_t n_reads);
@@ -116,6 +120,12 @@ int apc_exact_solid(apc_ctx *ctx, uint8_t k, float lc_adjusted, uint64_t solid_k
  * read, as in :584.  Host in, host out; H2D/D2H inside the call. */
 int apc_approx_count(apc_ctx *ctx, uint8_t k, const uint64_t *kmers,
                      uint32_t n_kmers, uint64_t *counts_out);
+/* Same, enqueued on the context's stream without waiting: counts_out is
+ * filled once apc_sync returns.  `kmers` is consumed before the call returns.
+ * Two contexts on one device (e.g. read starts and read ends) overlap the
+ * upload of one sample with the scan of the other this way. */
+int apc_approx_count_async(apc_ctx *ctx, uint8_t k, const uint64_t *kmers,
+                           uint32_t n_kmers, uint64_t *counts_out);
 
 /* Split-phase form of the same call for resident data and multi-GPU use:
  * set_queries uploads the match tables, scan launches the kernel on the

@@ -146,3 +146,34 @@ def test_many_kmers_many_reads_split_phase(counter):
     assert np.array_equal(again, want)
     t = counter.timing()
     assert t["scan_ms"] > 0 and t["scan_launches"] == 1
+
+
+def test_async_api_two_contexts(built):
+    """apc_upload_sample_async + apc_approx_count_async on two contexts (starts / ends),
+    page-locked buffers, results valid after apc_sync; repeated with changing inputs."""
+    import torch
+    from approx_counter_b200 import ApproxCounter
+    rng = np.random.default_rng(21)
+    k = 16
+    ctxs = [ApproxCounter(0), ApproxCounter(0)]
+    try:
+        for rep in range(3):
+            samples = [make_sample(rng, 1500 + 100 * rep, 100 + i, k) for i in range(2)]
+            kmers = [make_kmers(rng, k, 40 + rep) for _ in range(2)]
+            pin_s = [torch.from_numpy(s).pin_memory() for s in samples]
+            pin_q = [torch.from_numpy(q.view(np.int64)).pin_memory() for q in kmers]
+            pin_o = [torch.zeros(len(q), dtype=torch.int64).pin_memory() for q in kmers]
+            for c, s, q, o in zip(ctxs, pin_s, pin_q, pin_o):
+                c.upload_sample_ptr_async(s.data_ptr(), s.shape[0], s.shape[1])
+                c.errorCount_ptr_async(q.data_ptr(), q.numel(), k, o.data_ptr())
+            for c in ctxs:
+                c.sync()
+            for s, q, o in zip(samples, kmers, pin_o):
+                codes, offs = orc.encode_matrix(s)
+                want = orc.error_count(codes, offs, q, k, fast=True)
+                assert np.array_equal(o.numpy().view(np.uint64), want)
+            t = ctxs[0].timing()
+            assert t["upload_ms"] > 0 and t["total_ms"] > 0
+    finally:
+        for c in ctxs:
+            c.close()
