@@ -4,10 +4,14 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <numeric>
 #include <random>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace apch {
 
@@ -164,62 +168,209 @@ bool parse_config(const std::string &path, std::vector<std::pair<std::string, st
 }
 
 // ---- FASTA / FASTQ ---------------------------------------------------------------
+// Replaces SeqFileIn + readRecords (:819-825).  The whole file is read into one buffer,
+// cut into one piece per host thread at record boundaries, and every piece compacts its
+// sequence letters IN PLACE towards the start of the piece with memchr/memmove (no
+// per-character work on the fast path, no second copy of the data); the gaps between the
+// pieces are then closed front to back.  Multi-line records, CRLF and blank lines are
+// accepted; ids and qualities are dropped.
+namespace {
+
+struct Piece {
+    char *begin = nullptr;  // piece region; compacted letters end up at [begin, begin + n_bases)
+    const char *end = nullptr;
+    uint64_t n_bases = 0;
+    std::vector<uint64_t> lens;
+    bool ok = true;
+    std::string err;
+};
+
+inline const char *line_end(const char *p, const char *end) {
+    const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+    return nl ? nl : end;
+}
+
+// move the letters of the line [p, e) (without its '\n') to w; returns how many were taken.
+// w <= p always holds (compaction only moves bytes towards the front).
+inline uint64_t take_line(char *w, const char *p, const char *e) {
+    while (e > p && (e[-1] == '\r' || e[-1] == ' ' || e[-1] == '\t')) e--;
+    const size_t n = (size_t)(e - p);
+    if (n == 0) return 0;
+    if (!memchr(p, ' ', n) && !memchr(p, '\t', n) && !memchr(p, '\r', n)) {
+        if (w != p) memmove(w, p, n);
+        return n;
+    }
+    uint64_t taken = 0;
+    for (; p < e; p++)
+        if (*p != ' ' && *p != '\t' && *p != '\r') w[taken++] = *p;
+    return taken;
+}
+
+inline const char *skip_blank(const char *p, const char *end) {
+    while (p < end && (*p == '\n' || *p == '\r' || *p == ' ' || *p == '\t')) p++;
+    return p;
+}
+
+// parse whole records from the piece; `fastq` selects the grammar
+void parse_piece(Piece &pc, bool fastq) {
+    const char *p = pc.begin, *end = pc.end;
+    char *w = pc.begin;
+    while (true) {
+        p = skip_blank(p, end);
+        if (p >= end) break;
+        if (*p != (fastq ? '@' : '>')) {
+            pc.ok = false;
+            pc.err = fastq ? "malformed FASTQ record" : "malformed FASTA record";
+            return;
+        }
+        p = line_end(p, end); // header line
+        if (p < end) p++;
+        uint64_t n = 0;
+        const char stop = fastq ? '+' : '>';
+        while (p < end && *p != stop) {
+            const char *e = line_end(p, end);
+            const uint64_t got = take_line(w, p, e);
+            w += got;
+            n += got;
+            p = e < end ? e + 1 : end;
+        }
+        if (fastq) {
+            if (p >= end) { pc.ok = false; pc.err = "truncated FASTQ record"; return; }
+            p = line_end(p, end); // '+' line
+            if (p < end) p++;
+            uint64_t q = 0; // the quality string may contain '@' and '>': count characters
+            while (p < end && q < n) {
+                const char *e = line_end(p, end);
+                const char *t = e;
+                while (t > p && t[-1] == '\r') t--;
+                q += (uint64_t)(t - p);
+                p = e < end ? e + 1 : end;
+            }
+        }
+        pc.lens.push_back(n);
+    }
+    pc.n_bases = (uint64_t)(w - pc.begin);
+}
+
+// first record start at or after `p` (a position inside the file)
+const char *next_record(const char *begin, const char *p, const char *end, bool fastq) {
+    if (p <= begin) return begin;
+    p = line_end(p - 1, end); // move to a line start
+    if (p < end) p++;
+    while (p < end) {
+        if (!fastq) {
+            if (*p == '>') return p;
+        } else if (*p == '@') {
+            // a header is a line starting with '@' whose second-next line starts with '+'
+            // (4-line FASTQ; a quality line starting with '@' is followed by a header, whose
+            // second-next line is a sequence and cannot start with '+')
+            const char *l1 = line_end(p, end);
+            if (l1 < end) {
+                const char *l2 = line_end(l1 + 1, end);
+                if (l2 < end && l2 + 1 < end && l2[1] == '+') return p;
+            }
+        }
+        p = line_end(p, end);
+        if (p < end) p++;
+    }
+    return end;
+}
+
+} // namespace
+
 bool read_fastx(const std::string &path, Reads &out, std::string &err) {
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) {
         err = "could not open " + path;
         return false;
     }
-    std::string data;
-    {
-        char buf[1 << 16];
-        size_t n;
-        while ((n = fread(buf, 1, sizeof buf, f)) > 0) data.append(buf, n);
+    // one read of the whole file into an uninitialised buffer (grown if the input is a pipe)
+    size_t cap = 1 << 16, size = 0;
+    if (fseek(f, 0, SEEK_END) == 0) {
+        const long fsize = ftell(f);
+        if (fsize > 0) cap = (size_t)fsize + 1;
+        fseek(f, 0, SEEK_SET);
+    }
+    std::unique_ptr<char[]> buf(new char[cap]);
+    for (;;) {
+        if (size == cap) {
+            std::unique_ptr<char[]> bigger(new char[cap * 2]);
+            memcpy(bigger.get(), buf.get(), size);
+            buf.swap(bigger);
+            cap *= 2;
+        }
+        const size_t n = fread(buf.get() + size, 1, cap - size, f);
+        if (n == 0) break;
+        size += n;
     }
     fclose(f);
-    out.bases.clear();
+    out.storage.reset();
+    out.n_bases = 0;
     out.offsets.assign(1, 0);
-    out.bases.reserve(data.size());
-    const char *p = data.data(), *end = p + data.size();
-    auto skip_ws = [&]() { while (p < end && (*p == '\n' || *p == '\r' || *p == ' ' || *p == '\t')) p++; };
-    auto skip_line = [&]() { while (p < end && *p != '\n') p++; if (p < end) p++; };
-    auto take_line = [&](uint64_t &taken) { // append the letters of one line
-        while (p < end && *p != '\n') {
-            if (*p != '\r' && *p != ' ' && *p != '\t') { out.bases.push_back(*p); taken++; }
-            p++;
-        }
-        if (p < end) p++;
-    };
-    skip_ws();
-    if (p >= end) return true; // empty file: no records
-    const char first = *p;
-    if (first != '>' && first != '@') {
+    char *begin = buf.get(), *end = begin + size;
+    char *p0 = const_cast<char *>(skip_blank(begin, end));
+    if (p0 >= end) return true; // empty file: no records
+    if (*p0 != '>' && *p0 != '@') {
         err = "unrecognised sequence file format (expected FASTA '>' or FASTQ '@')";
         return false;
     }
-    while (p < end) {
-        skip_ws();
-        if (p >= end) break;
-        if (first == '>') {
-            if (*p != '>') { err = "malformed FASTA record"; return false; }
-            skip_line();
-            uint64_t n = 0;
-            while (p < end && *p != '>') take_line(n);
-        } else {
-            if (*p != '@') { err = "malformed FASTQ record"; return false; }
-            skip_line();
-            uint64_t n = 0;
-            while (p < end && *p != '+') take_line(n);
-            if (p >= end) { err = "truncated FASTQ record"; return false; }
-            skip_line(); // '+' line
-            uint64_t q = 0;
-            while (p < end && q < n) { // quality may contain '@' and '>' — count characters
-                while (p < end && *p != '\n') { if (*p != '\r') q++; p++; }
-                if (p < end) p++;
-            }
+    const bool fastq = *p0 == '@';
+
+    int n_pieces = 1;
+#ifdef _OPENMP
+    n_pieces = omp_get_max_threads();
+#endif
+    // parsing is memory-bound: one piece per 32 MB is enough, more threads only add wake-up cost
+    size_t piece_bytes = (size_t)1 << 25;
+    if (const char *env = getenv("APCH_PIECE_BYTES")) piece_bytes = std::max<size_t>(1, strtoull(env, nullptr, 10)); // tests
+    n_pieces = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_pieces, size / piece_bytes));
+    auto cut_pieces = [&](int n, std::vector<Piece> &pieces) {
+        pieces.assign((size_t)n, Piece());
+        const char *prev = p0;
+        for (int i = 0; i < n; i++) {
+            const char *next = end;
+            if (i + 1 < n) next = std::max(prev, next_record(begin, begin + size / (size_t)n * (size_t)(i + 1), end, fastq));
+            pieces[(size_t)i].begin = const_cast<char *>(prev);
+            pieces[(size_t)i].end = next;
+            prev = next;
         }
-        out.offsets.push_back(out.bases.size());
+    };
+    std::vector<Piece> pieces;
+    if (n_pieces > 1) {
+        // dry run on record boundaries only: a piece must start with a record marker and the
+        // in-place compaction below cannot be undone, so unusual files (multi-line FASTQ whose
+        // quality lines defeat the boundary heuristic) are detected first by a cheap check
+        cut_pieces(n_pieces, pieces);
+        for (const Piece &pc : pieces)
+            if (pc.begin < pc.end && *pc.begin != (fastq ? '@' : '>')) n_pieces = 1;
     }
+    cut_pieces(n_pieces, pieces);
+#pragma omp parallel for schedule(static, 1)
+    for (int i = 0; i < n_pieces; i++) parse_piece(pieces[(size_t)i], fastq);
+    for (const Piece &pc : pieces)
+        if (!pc.ok) {
+            err = pc.err;
+            return false;
+        }
+    // close the gaps between pieces, front to back (destinations never overtake sources)
+    size_t total_reads = 0;
+    char *w = begin;
+    for (Piece &pc : pieces) {
+        if (pc.n_bases && w != pc.begin) memmove(w, pc.begin, pc.n_bases);
+        w += pc.n_bases;
+        total_reads += pc.lens.size();
+    }
+    out.n_bases = (uint64_t)(w - begin);
+    out.offsets.resize(total_reads + 1);
+    uint64_t off = 0;
+    size_t r = 0;
+    for (const Piece &pc : pieces)
+        for (uint64_t len : pc.lens) {
+            out.offsets[r++] = off;
+            off += len;
+        }
+    out.offsets[total_reads] = off;
+    out.storage = std::move(buf);
     return true;
 }
 

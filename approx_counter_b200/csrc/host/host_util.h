@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -44,11 +45,13 @@ bool parse_config(const std::string &path, std::vector<std::pair<std::string, st
 
 // :819-825 — all records of a FASTA/FASTQ file (ids and qualities dropped)
 struct Reads {
-    std::string bases;             // concatenated sequences (ASCII as read)
+    // the file's own buffer: sequences are compacted in place (no second copy of the data)
+    std::unique_ptr<char[]> storage;
+    uint64_t n_bases = 0;          // bytes of `storage` that hold sequence letters (ASCII as read)
     std::vector<uint64_t> offsets; // n+1
     uint64_t size() const { return offsets.empty() ? 0 : offsets.size() - 1; }
     uint64_t length(uint64_t i) const { return offsets[i + 1] - offsets[i]; }
-    const char *seq(uint64_t i) const { return bases.data() + offsets[i]; }
+    const char *seq(uint64_t i) const { return storage.get() + offsets[i]; }
 };
 bool read_fastx(const std::string &path, Reads &out, std::string &err);
 

@@ -144,7 +144,14 @@ def cpu_leg(w, ends, queries, target_s, threads=0):
     reference's `omp for schedule(dynamic)` :567) on the first R reads of both ends."""
     from oracle import orc
     k = w["k"]
-    nthreads = orc.num_threads() if threads <= 0 else threads
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: size the team from the CPUs this
+    # process may run on, not from the OpenMP default
+    if threads <= 0:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    nthreads = threads
 
     def run(r):
         cols = 0

@@ -152,3 +152,65 @@ def test_cli_flag_surface_without_gpu(built, tmp_path):
     if not torch.cuda.is_available():
         r = run_cli("-k", "4", "-sl", "10", str(fa))
         assert r.returncode == 2 and "cannot open CUDA device" in r.stderr   # no CPU fallback
+
+
+def _py_parse(text):
+    """Straightforward reference parser (multi-line FASTA, 4-line or multi-line FASTQ)."""
+    lines = text.replace("\r", "").split("\n")
+    seqs, i = [], 0
+    while i < len(lines):
+        ln = lines[i].strip()
+        if not ln:
+            i += 1
+            continue
+        if ln[0] == ">":
+            i += 1
+            s = ""
+            while i < len(lines) and not lines[i].startswith(">"):
+                s += lines[i].replace(" ", "").replace("\t", "")
+                i += 1
+            seqs.append(s)
+        else:
+            assert ln[0] == "@"
+            i += 1
+            s = ""
+            while not lines[i].startswith("+"):
+                s += lines[i].strip()
+                i += 1
+            i += 1
+            q = 0
+            while q < len(s):
+                q += len(lines[i])
+                i += 1
+            seqs.append(s)
+    return seqs
+
+
+@pytest.mark.parametrize("kind", ["fasta_multiline", "fastq_at_quality", "fasta_crlf"])
+def test_parallel_parser_pieces(host, tmp_path, kind, monkeypatch):
+    """The file is cut into pieces at record boundaries and compacted in place; tiny pieces
+    force many cuts through multi-line records, CRLF and quality lines starting with '@'."""
+    rng = np.random.default_rng(8)
+    recs = []
+    for i in range(3000):
+        n = int(rng.integers(0, 300))
+        s = "".join("ACGTN"[int(x)] for x in rng.integers(0, 5, n))
+        if kind == "fasta_multiline":
+            body = "\n".join(s[j:j + 60] for j in range(0, max(n, 1), 60))
+            recs.append(f">r{i} desc > @ +\n{body}\n" + ("\n" if i % 50 == 0 else ""))
+        elif kind == "fasta_crlf":
+            recs.append(f">r{i}\r\n{s}\r\n")
+        else:
+            qual = "".join("@+>I#"[int(x)] for x in rng.integers(0, 5, n))
+            if n:
+                qual = "@" + qual[1:]          # every quality line starts with '@'
+            recs.append(f"@r{i} x\n{s}\n+\n{qual}\n")
+    text = "".join(recs)
+    path = tmp_path / "x.fx"
+    path.write_text(text, newline="")
+    want = _py_parse(text)
+    for piece in ("1000000000", "4096", "65536"):
+        monkeypatch.setenv("APCH_PIECE_BYTES", piece)
+        r = host.Reads(path)
+        got = [r.seq(i).decode() for i in range(len(r))]
+        assert got == want
