@@ -420,16 +420,17 @@ def run_b200(args, w):
     if 4.0 * cols_launch / per_launch_s > issue_peak:
         raise SystemExit("bench.py: implausible kernel time — the timed region did not contain the scan kernel")
     achieved = ALGO_OPS_PER_COLUMN * cols_launch / per_launch_s
-    traffic = None
-    try:
+    traffic = ncu_alu = None
+    try:  # figures from the committed ncu capture of this kernel on this workload (profiles/)
         prof = json.load(open(os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")))
         traffic = prof.get(args.workload, {}).get("dram_bytes_per_launch")
+        ncu_alu = prof.get(args.workload, {}).get("alu_pipe_pct")
     except Exception:
         pass
     hbm_bytes_launch = n * (sl + 0.5) + 80 * ((q_start + 7) // 8) + 8 * q_start  # tiles (1 B/base) + tables + counts
     roofline = {
         "bound": "int-alu", "kernel": "approx_scan_kernel", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
-        "unit": "Tint-op/s", "frac": achieved / alu_peak, "traffic": traffic,
+        "unit": "Tint-op/s", "frac": achieved / alu_peak, "traffic": traffic, "ncu_alu_pipe_pct": ncu_alu,
         "peak_source": f"ALU pipe nominal = {sms} SM x 4 SMSP x 16 lanes/clk x {sm_max:.0f} MHz (SURVEY.md §8d)",
         "algorithmic_ops_per_column": ALGO_OPS_PER_COLUMN, "columns_per_launch": cols_launch,
         "avg_launch_ms": per_launch_s * 1e3, "launches_timed": n_launch,
