@@ -61,16 +61,22 @@ enum { CNT_KEYS = 0, CNT_HAD_N = 1, CNT_SELECTED = 2, CNT_SLOTS = 8 };
 // sum over the 16 dimer bins of v*(v-1) for the k-1 overlapping dimers of a
 // k-mer (:216-231).  Direct form, used on the distinct k-mers in K5.
 __device__ __forceinline__ uint32_t dimer_sum_direct(uint64_t kmer, int k) {
-    unsigned long long lo = 0, hi = 0; // 16 byte-wide bins
+    // E[c]: bit 2i set iff base i (2-bit field at bit 2i) equals c.  The dimer read at
+    // field i (:219 `kmer & 15` after i shifts) is (base i+1, base i) = hi*4 + lo, so its
+    // count is popc(E[lo] & (E[hi] >> 2)) over the k-1 dimer positions.
+    const uint64_t lo_bits = 0x5555555555555555ull;
+    const uint64_t b0 = kmer & lo_bits, b1 = (kmer >> 1) & lo_bits;
+    const uint64_t valid = k >= 33 ? lo_bits : (lo_bits & ((1ull << (2 * (k - 1))) - 1ull)); // positions 0..k-2
+    const uint64_t e[4] = {~b1 & ~b0 & lo_bits, ~b1 & b0, b1 & ~b0 & lo_bits, b1 & b0};
     uint32_t sum = 0;
-    for (int i = 0; i < k - 1; i++) {
-        const uint32_t idx = (uint32_t)kmer & 15u;
-        kmer >>= 2;
-        const uint32_t sh = (idx & 7u) * 8u;
-        const unsigned long long w = (idx & 8u) ? hi : lo;
-        sum += 2u * (uint32_t)((w >> sh) & 0xFFu); // (c+1)c - c(c-1) = 2c
-        const unsigned long long inc = 1ull << sh;
-        if (idx & 8u) hi += inc; else lo += inc;
+#pragma unroll
+    for (int hi = 0; hi < 4; hi++) {
+        const uint64_t eh = (e[hi] >> 2) & valid;
+#pragma unroll
+        for (int lo = 0; lo < 4; lo++) {
+            const uint32_t v = (uint32_t)__popcll(e[lo] & eh);
+            sum += v * (v - 1u);
+        }
     }
     return sum;
 }
@@ -272,6 +278,7 @@ dimer_sums_kernel(const K *__restrict__ uniq, const uint64_t d, const int k, uin
 }
 
 // histogram of one 8-bit digit of count(i) over the entries whose higher digits match
+// (shift == 0xFFFFFFFF: histogram of min(count, 255) over all entries)
 __global__ void __launch_bounds__(kPassThreads)
 count_digit_hist_kernel(const uint32_t *__restrict__ start, const uint64_t d, const uint32_t prefix_mask,
                         const uint32_t prefix_val, const uint32_t shift, unsigned long long *__restrict__ hist) {
@@ -290,7 +297,7 @@ count_digit_hist_kernel(const uint32_t *__restrict__ start, const uint64_t d, co
                 const uint32_t c = s1 - s0;
                 s0 = s1;
                 if ((c & prefix_mask) == prefix_val) {
-                    const uint32_t b = (c >> shift) & 0xFFu;
+                    const uint32_t b = shift == 0xFFFFFFFFu ? min(c, 255u) : (c >> shift) & 0xFFu;
                     if (b != bin) {
                         if (runlen) atomicAdd(&s_hist[bin], runlen);
                         bin = b;
@@ -567,7 +574,29 @@ int run_exact(Ctx *c, int k, uint32_t lc_min_sum, uint64_t lim, uint64_t solid_k
         uint64_t need = lim; // rank still to be located inside the current prefix class
         uint32_t prefix_mask = 0, prefix_val = 0;
         uint64_t class_size = d;
-        for (int shift = 24; shift >= 0; shift -= 8) {
+        // Fast path: counts are small for almost every k-mer.  One histogram of min(count, 255)
+        // settles the threshold whenever fewer than `lim` k-mers have a count >= 255.
+        bool settled = false;
+        {
+            APC_CUDA(c, cudaMemsetAsync(x.d_hist, 0, 256 * sizeof(unsigned long long), s));
+            count_digit_hist_kernel<<<d_blocks, kPassThreads, 0, s>>>(x.d_start, d, 0u, 0u, 0xFFFFFFFFu, x.d_hist);
+            APC_CUDA(c, cudaGetLastError());
+            x.launches++;
+            if ((st = read_hist(256))) return st;
+            if (h_hist[255] < need) {
+                int digit = 254;
+                uint64_t above = h_hist[255];
+                for (; digit > 0; digit--) {
+                    if (above + h_hist[digit] >= need) break;
+                    above += h_hist[digit];
+                }
+                need -= above;
+                class_size = h_hist[digit];
+                prefix_val = (uint32_t)digit;
+                settled = true;
+            }
+        }
+        for (int shift = settled ? -8 : 24; shift >= 0; shift -= 8) {
             APC_CUDA(c, cudaMemsetAsync(x.d_hist, 0, 256 * sizeof(unsigned long long), s));
             count_digit_hist_kernel<<<d_blocks, kPassThreads, 0, s>>>(x.d_start, d, prefix_mask, prefix_val,
                                                                       (uint32_t)shift, x.d_hist);

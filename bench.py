@@ -120,10 +120,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def make_ends(w, first, pinned_torch=None):
+def make_ends(w, first, pinned_torch=None, count=None):
     """Sampled starts and ends of synthetic reads [first, first+n): uint8[n, sl], uint8[n, sl+1]."""
     from approx_counter_b200 import host
-    n, sl = w["n"], w["sl"]
+    n, sl = (w["n"] if count is None else count), w["sl"]
     if pinned_torch is not None:
         torch = pinned_torch
         t0 = torch.empty((n, sl), dtype=torch.uint8, pin_memory=True)
@@ -266,7 +266,14 @@ def run_b200(args, w):
     torch.cuda.set_stream(stream)
 
     # ---- inputs: this rank's shard of the synthetic read stream, in pinned host memory
-    (h_start, h_end), pinned = make_ends(w, rank * n, pinned_torch=torch)
+    if args.scaling == "strong":
+        # one job of n reads split over the ranks (contiguous blocks of 32-read tiles)
+        from approx_counter_b200 import shard_bounds
+        lo, hi = shard_bounds(n, rank, world)
+        n_total, first, n = n, lo, hi - lo
+    else:
+        n_total, first = n * world, rank * n
+    (h_start, h_end), pinned = make_ends(w, first, pinned_torch=torch, count=n)
     ends = (h_start, h_end)
     ctxs = [ApproxCounter(local_rank), ApproxCounter(local_rank)]
     for c, s in zip(ctxs, ends):
@@ -348,8 +355,8 @@ def run_b200(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, kern_ms = float(t[0]), float(t[1])
 
-    cols_rank = columns_per_step(w, q_start, q_end)
-    cols_job = cols_rank * world
+    cols_rank = q_start * n * sl + q_end * n * (sl + 1)
+    cols_job = q_start * n_total * sl + q_end * n_total * (sl + 1)
     value = k * cols_job * args.steps / (dev_ms / 1e3) / 1e9
     final_counts = [c.cpu().numpy().view(np.uint64).copy() for c in counts]
 
@@ -470,10 +477,10 @@ def run_b200(args, w):
 
     line = {
         "metric": "approx_count_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": w["text"] + ", both ends (start n x sl, end n x (sl+1))", "k": k,
-                   "reads_per_gpu": n, "sl": sl, "lim": lim, "queries": [q_start, q_end], "seed": w["seed"],
+                   "reads_per_gpu": n, "reads_total": n_total, "sl": sl, "lim": lim, "queries": [q_start, q_end], "seed": w["seed"],
                    "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset outside the event pairs)",
                    "parallelism": f"reads sharded over {world} GPU(s), one all-reduce of Q u64 per end"},
         "queries_per_s": (q_start + q_end) * args.steps / (dev_ms / 1e3),
@@ -509,6 +516,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="C2")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: every rank holds its own n-read shard (default); strong: one n-read job split over the ranks")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size, seconds of CPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
