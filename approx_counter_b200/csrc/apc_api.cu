@@ -384,11 +384,6 @@ int apc_set_option(apc_ctx *c, const char *name, int64_t value) {
         c->opt_tiles_per_job = (int)value;
         return APC_OK;
     }
-    if (!std::strcmp(name, "scan_min_blocks")) {
-        if (value != 3 && value != 4) return apc::fail(c, APC_ERR_INVALID, "scan_min_blocks must be 3 or 4");
-        c->opt_min_blocks = (int)value;
-        return APC_OK;
-    }
     if (!std::strcmp(name, "scan_first_read")) {
         if (value < 0 || value % apc::kTileReads) return apc::fail(c, APC_ERR_INVALID, "scan_first_read must be a multiple of 32");
         c->opt_first_read = (uint64_t)value;

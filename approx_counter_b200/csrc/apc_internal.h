@@ -32,6 +32,7 @@ struct ScanVariant {
     int nw; // u32 words per unit (1 or 2)
     int f;  // k-mers interleaved per unit
     int queries_per_group() const { return f * kWordsPerThread / nw; }
+    int rows_per_unit() const { return 32 * nw / f; } // complete k-mer rows a unit can hold
 };
 
 // device scratch of the exact stage (exact_kernels.cu); grown on demand, kept
@@ -97,7 +98,6 @@ struct Ctx {
     // options
     int opt_variant = 0;
     int opt_tiles_per_job = 0;
-    int opt_min_blocks = 3;       // resident CTAs per SM the scan kernel is compiled for (3: 80 regs, 4: 64 regs)
     uint64_t opt_first_read = 0;  // scan only reads [first, first+n) of the resident sample
     int64_t opt_n_reads = -1;     // -1 = to the end
 

@@ -137,6 +137,34 @@ __device__ __forceinline__ void step1(ScanState &st, const uint4 eq, const uint3
     }
 }
 
+__device__ __forceinline__ uint4 lds_row(const uint32_t *table, const uint32_t off) {
+    return *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(table) + off);
+}
+
+// 2*T columns, one 3-input OR per level and word for all of them.  When the unit has
+// spare rows above row k-1 (k smaller than the rows the unit can hold) the match tables
+// mark those rows "always equal", so a hit in row k-1 keeps moving up one row per column
+// instead of being shifted out: the accumulator then only has to look at every T-th
+// column (T - 1 <= spare rows) and the per-column cost of hit accumulation drops from
+// 1.5 LOP3 to 1.5 / T.  Bits that reach the spare rows at levels 1 and 2 through the
+// other transitions are hits of the same or an earlier column at the same or a lower
+// level, so any set bit in rows >= k-1 of an accumulator is a genuine hit.
+template <int NW, int T>
+__device__ __forceinline__ void stepT(ScanState &st, const uint32_t *table, const uint32_t (&off)[2 * T],
+                                      const uint32_t mul, const uint32_t m) {
+    uint32_t p0[4], p1[4], p2[4], n0[4], n1[4], n2[4];
+#pragma unroll
+    for (int c = 0; c < T; c++) Column<NW>::core(st, lds_row(table, off[c]), mul, m, p0, p1, p2);
+#pragma unroll
+    for (int c = T; c < 2 * T; c++) Column<NW>::core(st, lds_row(table, off[c]), mul, m, n0, n1, n2);
+#pragma unroll
+    for (int w = NW - 1; w < 4; w += NW) {
+        st.a0[w] = or3(st.a0[w], p0[w], n0[w]);
+        st.a1[w] = or3(st.a1[w], p1[w], n1[w]);
+        st.a2[w] = or3(st.a2[w], p2[w], n2[w]);
+    }
+}
+
 // Two columns, one 3-input OR per level and word.
 template <int NW>
 __device__ __forceinline__ void step2(ScanState &st, const uint4 eqa, const uint4 eqb, const uint32_t mul,

@@ -65,6 +65,21 @@ void build_peq_tables(const uint64_t *kmers, uint32_t n_kmers, int k, ScanVarian
     const uint32_t qg = v.queries_per_group();
     n_groups = (n_kmers + qg - 1) / qg;
     std::fill(table, table + (size_t)n_groups * kPeqRows * kWordsPerThread, 0u);
+    // spare rows k .. rows_per_unit-1 compare equal to EVERY text code (N and padding
+    // included): they are the delay line of stepT
+    const int rows = v.rows_per_unit();
+    if (rows > k) {
+        uint32_t unit_mask[2] = {0u, 0u};
+        for (int i = k; i < rows; i++)
+            for (int f = 0; f < v.f; f++) {
+                const int bit = i * v.f + f;
+                unit_mask[bit / 32] |= 1u << (bit % 32);
+            }
+        for (uint32_t g = 0; g < n_groups; g++)
+            for (int c = 0; c < kPeqRows; c++)
+                for (int w = 0; w < kWordsPerThread; w++)
+                    table[((size_t)g * kPeqRows + c) * kWordsPerThread + w] = unit_mask[w % v.nw];
+    }
     for (uint32_t q = 0; q < n_kmers; q++) {
         const uint32_t g = q / qg, r = q % qg, u = r / v.f, f = r % v.f;
         uint32_t *t = table + (size_t)g * kPeqRows * kWordsPerThread;
@@ -74,10 +89,6 @@ void build_peq_tables(const uint64_t *kmers, uint32_t n_kmers, int k, ScanVarian
             t[c * kWordsPerThread + u * v.nw + bit / 32] |= 1u << (bit % 32);
         }
     }
-}
-
-__device__ __forceinline__ uint4 lds_row(const uint32_t *table, const uint32_t off) {
-    return *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(table) + off);
 }
 
 __device__ __forceinline__ uint4 ldg_tile(const uint4 *p) { return __ldg(p); }
@@ -90,6 +101,7 @@ __device__ __forceinline__ uint4 ldg_tile(const uint4 *p) { return __ldg(p); }
 // its current group; the slot index is merged into the table offset by the same PRMT that
 // extracts the text byte, so a column still costs one PRMT + one LDS.128 per thread.
 constexpr int kSlotBytes = 256;
+constexpr int kScanBlocksPerSM = 3; // 76-80 registers, 6 warps per SMSP (4 CTAs of 64 registers measured slower)
 constexpr uint32_t kMaxTilesPerJob = 64; // 3 hits x 64 tiles < 256: the packed byte counters cannot overflow
 
 template <int F>
@@ -97,12 +109,12 @@ __device__ __forceinline__ constexpr uint32_t kFieldMask() {
     return F == 1 ? 0x000001u : F == 2 ? 0x000101u : 0x010101u;
 }
 
-template <int NW, int F, int MB>
-__global__ void __launch_bounds__(kScanWarps * 32, MB)
+template <int NW, int F, int T>
+__global__ void __launch_bounds__(kScanWarps * 32, kScanBlocksPerSM)
 approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, const uint64_t n_reads,
                    const uint32_t chunks, const uint32_t read_len, const uint32_t *__restrict__ peq,
                    const uint32_t n_groups, const uint32_t tiles_per_job, const uint32_t n_jobs,
-                   const uint32_t mul, const uint32_t top_shift, const uint32_t n_kmers,
+                   const uint32_t mul, const uint32_t top_shift, const uint32_t hit_rows, const uint32_t n_kmers,
                    unsigned long long *__restrict__ counts, unsigned int *__restrict__ job_counter) {
     constexpr int UNITS = kWordsPerThread / NW;
     constexpr int ACC0 = NW - 1; // word of a unit that holds row k-1
@@ -149,13 +161,23 @@ approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, cons
                 p += kTileReads;
                 const uint4 nxt = ldg_tile(p);
                 const uint32_t tw[4] = {v.x, v.y, v.z, v.w};
+                // table offset = slot * 256 + code byte: byte j of tw, byte 0 of `warp`, then zeros (bytes 1 of `warp`)
+                if (T == 1) {
 #pragma unroll
-                for (int wi = 0; wi < 4; wi++) {
-                    // table offset = slot * 256 + code byte: byte j of tw, byte 0 of `warp`, then zeros (bytes 1 of `warp`)
-                    const uint32_t o0 = __byte_perm(tw[wi], warp, 0x5540u), o1 = __byte_perm(tw[wi], warp, 0x5541u);
-                    const uint32_t o2 = __byte_perm(tw[wi], warp, 0x5542u), o3 = __byte_perm(tw[wi], warp, 0x5543u);
-                    step2<NW>(st, lds_row(s_peq, o0), lds_row(s_peq, o1), mul, m);
-                    step2<NW>(st, lds_row(s_peq, o2), lds_row(s_peq, o3), mul, m);
+                    for (int wi = 0; wi < 4; wi++) {
+                        const uint32_t o0 = __byte_perm(tw[wi], warp, 0x5540u), o1 = __byte_perm(tw[wi], warp, 0x5541u);
+                        const uint32_t o2 = __byte_perm(tw[wi], warp, 0x5542u), o3 = __byte_perm(tw[wi], warp, 0x5543u);
+                        step2<NW>(st, lds_row(s_peq, o0), lds_row(s_peq, o1), mul, m);
+                        step2<NW>(st, lds_row(s_peq, o2), lds_row(s_peq, o3), mul, m);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2 * T) {
+                        uint32_t og[2 * T];
+#pragma unroll
+                        for (int c = 0; c < 2 * T; c++) og[c] = __byte_perm(tw[(j + c) >> 2], warp, 0x5540u + ((j + c) & 3));
+                        stepT<NW, T>(st, s_peq, og, mul, m);
+                    }
                 }
                 v = nxt;
             }
@@ -189,9 +211,19 @@ approx_scan_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, cons
 #pragma unroll
             for (int u = 0; u < UNITS; u++) {
                 const int w = u * NW + ACC0;
-                // rows past k-1 may hold junk at levels 1 and 2: keep the F bits of row k-1 only
-                const uint32_t lo = ((st.a0[w] ^ st.a1[w] ^ st.a2[w]) >> top_shift) & ((1u << F) - 1u);
-                const uint32_t hi = (st.a1[w] >> top_shift) & ((1u << F) - 1u);
+                // any bit in rows k-1 .. k-2+hit_rows of an accumulator is a hit (stepT): fold
+                // those rows onto row k-1, then keep its F bits
+                uint32_t y[3] = {st.a0[w] >> top_shift, st.a1[w] >> top_shift, st.a2[w] >> top_shift};
+#pragma unroll
+                for (int e = 0; e < 3; e++) {
+                    if (T > 1 && hit_rows > 1) y[e] |= y[e] >> F; // warp-uniform branches (T == 1 <=> hit_rows == 1)
+                    if (T > 1 && hit_rows > 2) y[e] |= y[e] >> (2 * F);
+                    if (T > 1 && hit_rows > 4) y[e] |= y[e] >> (4 * F);
+                    if (T > 1 && hit_rows > 8) y[e] |= y[e] >> (8 * F);
+                    if (T > 1 && F == 1 && hit_rows > 16) y[e] |= y[e] >> 16;
+                    y[e] &= (1u << F) - 1u;
+                }
+                const uint32_t lo = y[0] ^ y[1] ^ y[2], hi = y[1];
                 // spread field f (bit f) to byte f: x * (1 + 2^7 + 2^14) & 0x010101
                 const uint32_t slo = (lo * 0x4081u) & kFieldMask<F>(), shi = (hi * 0x4081u) & kFieldMask<F>();
                 if (valid) cntw[u] += slo + 2u * shi;
@@ -216,7 +248,7 @@ struct ScanRange {
     uint64_t n_reads;   // reads in the range (relative to its first tile)
 };
 
-template <int NW, int F, int MB>
+template <int NW, int F, int T>
 static cudaError_t launch_variant(const Ctx &c, const ScanRange &r, unsigned long long *d_counts,
                                   uint32_t tiles_per_job) {
     const uint64_t jobs = (uint64_t)((r.n_tiles + tiles_per_job - 1) / tiles_per_job) * c.n_groups;
@@ -225,11 +257,13 @@ static cudaError_t launch_variant(const Ctx &c, const ScanRange &r, unsigned lon
     const uint32_t mul = 1u << F;
     uint32_t top = (uint32_t)(c.k - 1) * F;
     if (NW == 2) top -= 32; // relative to the high word
-    const uint64_t wave = (uint64_t)c.sm_count * MB;
+    const uint64_t wave = (uint64_t)c.sm_count * kScanBlocksPerSM;
     const unsigned grid = (unsigned)std::min<uint64_t>(wave, (jobs + kScanWarps - 1) / kScanWarps);
-    approx_scan_kernel<NW, F, MB><<<grid, kScanWarps * 32, 0, c.stream>>>(
+    // rows k-1 .. rows_per_unit-1 of an accumulator can hold hits (spare rows are the delay line)
+    const uint32_t hit_rows = (uint32_t)(c.variant.rows_per_unit() - c.k + 1);
+    approx_scan_kernel<NW, F, T><<<grid, kScanWarps * 32, 0, c.stream>>>(
         r.tiles, r.n_tiles, r.n_reads, c.chunks, c.max_len, c.d_peq, c.n_groups, tiles_per_job, (uint32_t)jobs, mul,
-        top, c.n_kmers, d_counts, c.d_job_counter);
+        top, hit_rows, c.n_kmers, d_counts, c.d_job_counter);
     return cudaGetLastError();
 }
 
@@ -254,7 +288,7 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
         // a job is tiles_per_job tiles x one k-mer group for ONE warp.  Aim for >= 64 jobs per
         // resident warp (tail <= 1/64 of the run) but keep jobs long enough (>= 2 tiles when
         // possible) that the table load and the count flush stay below 1 % of a job.
-        const uint64_t warps = (uint64_t)c.sm_count * (c.opt_min_blocks == 4 ? 4 : 3) * kScanWarps;
+        const uint64_t warps = (uint64_t)c.sm_count * kScanBlocksPerSM * kScanWarps;
         const uint64_t work = (uint64_t)r.n_tiles * c.n_groups;
         uint64_t t = work / (warps * 64);
         if (t < 1) t = 1;
@@ -263,14 +297,20 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
     }
     if (tpj > kMaxTilesPerJob) tpj = kMaxTilesPerJob;
     *launches = 1;
-    const bool mb4 = c.opt_min_blocks == 4;
-    if (c.variant.nw == 1 && c.variant.f == 1)
-        return mb4 ? launch_variant<1, 1, 4>(c, r, d_counts, tpj) : launch_variant<1, 1, 3>(c, r, d_counts, tpj);
-    if (c.variant.nw == 1 && c.variant.f == 2)
-        return mb4 ? launch_variant<1, 2, 4>(c, r, d_counts, tpj) : launch_variant<1, 2, 3>(c, r, d_counts, tpj);
-    if (c.variant.nw == 1 && c.variant.f == 3) return launch_variant<1, 3, 3>(c, r, d_counts, tpj);
-    if (c.variant.nw == 2 && c.variant.f == 3)
-        return mb4 ? launch_variant<2, 3, 4>(c, r, d_counts, tpj) : launch_variant<2, 3, 3>(c, r, d_counts, tpj);
+    // accumulator stride: every T-th column is enough when the unit has T-1 spare rows
+    const int spare = c.variant.rows_per_unit() - c.k;
+    const int t = spare >= 3 ? 4 : spare >= 1 ? 2 : 1;
+#define APC_LAUNCH(NW_, F_)                                                            \
+    do {                                                                               \
+        if (t == 4) return launch_variant<NW_, F_, 4>(c, r, d_counts, tpj);            \
+        if (t == 2) return launch_variant<NW_, F_, 2>(c, r, d_counts, tpj);            \
+        return launch_variant<NW_, F_, 1>(c, r, d_counts, tpj);                        \
+    } while (0)
+    if (c.variant.nw == 1 && c.variant.f == 1) APC_LAUNCH(1, 1);
+    if (c.variant.nw == 1 && c.variant.f == 2) APC_LAUNCH(1, 2);
+    if (c.variant.nw == 1 && c.variant.f == 3) APC_LAUNCH(1, 3);
+    if (c.variant.nw == 2 && c.variant.f == 3) APC_LAUNCH(2, 3);
+#undef APC_LAUNCH
     return cudaErrorInvalidValue;
 }
 

@@ -8,7 +8,7 @@ def run(c, n, L, k, q, variant=0, tpj=0, reps=5, mb=3):
     rng = np.random.default_rng(1)
     sample = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=(n, L))
     kmers = rng.integers(0, 1 << 62, q).astype(np.uint64) & np.uint64((1 << (2 * k)) - 1)
-    c.set_option("scan_variant", variant); c.set_option("tiles_per_job", tpj); c.set_option("scan_min_blocks", mb)
+    c.set_option("scan_variant", variant); c.set_option("tiles_per_job", tpj)
     c.upload_sample(sample); c.set_queries(kmers, k)
     best = 1e9
     for _ in range(reps):
@@ -24,8 +24,8 @@ if __name__ == "__main__":
             print(name, "%.4g" % c.microbench(name), flush=True)
         if len(sys.argv) > 1 and sys.argv[1] == "micro":
             sys.exit(0)
-        cases = [(100000, 100, 16, 2000, 0, 0, 5, 4), (200000, 150, 20, 2000, 0, 0, 5, 4), (200000, 200, 32, 2000, 0, 0, 5, 4),
-                 (100000, 100, 10, 2000, 0, 0, 5, 3),(10000, 100, 16, 500), (100000, 100, 16, 2000), (100000, 101, 16, 2000),
+        cases = [(100000, 100, 15, 2000), (100000, 100, 13, 2000), (100000, 100, 9, 2000), (100000, 100, 7, 2000),
+                 (200000, 150, 19, 2000), (200000, 150, 18, 2000), (200000, 150, 21, 2000), (200000, 200, 31, 2000), (200000, 200, 29, 2000),(10000, 100, 16, 500), (100000, 100, 16, 2000), (100000, 101, 16, 2000),
                  (100000, 100, 16, 2000, 0, 1), (100000, 100, 16, 2000, 0, 2), (100000, 100, 16, 2000, 0, 4),
                  (100000, 100, 16, 2000, 0, 8), (100000, 100, 16, 2000, 0, 32),
                  (100000, 100, 16, 2000, 1), (200000, 150, 20, 2000), (200000, 150, 20, 2000, 1),
