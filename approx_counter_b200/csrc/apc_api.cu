@@ -36,6 +36,9 @@ static int grow(Ctx *c, T *&ptr, size_t &cap, size_t need_bytes) {
         cap = 0;
     }
     if (need_bytes == 0) need_bytes = 16;
+    // 1/8 of slack: the `end` sample of a run is one base per read longer than the `start`
+    // sample (:463) and must not force a re-allocation of every buffer
+    need_bytes += need_bytes / 8;
     cudaError_t e = cudaMalloc((void **)&ptr, need_bytes);
     if (e != cudaSuccess) {
         ptr = nullptr;

@@ -14,6 +14,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "apc.h"
@@ -255,24 +256,29 @@ int cli_main(int argc, const char **argv) {
     int tab_level = 0;
     if (v > 0 && nb_of_runs > 1) std::cout << "\nA total of " << nb_of_runs << " runs will be performed." << std::endl;
 
-    // GPU contexts: no CPU fallback — fail loudly if the device is unusable
+    // GPU contexts: no CPU fallback — fail loudly if the device is unusable.  Creating a CUDA
+    // context takes about half a second, so it runs beside the parsing of the input file.
     if (n_gpus < 1) n_gpus = 1;
     std::vector<Gpu> gpus(n_gpus);
-    for (uint64_t g = 0; g < n_gpus; g++) {
-        const int st = apc_create((int)(device0 + g), &gpus[g].ctx);
-        if (st != APC_OK) return gpu_fail("cannot open CUDA device", nullptr, st);
-    }
-    apc_ctx *ctx0 = gpus[0].ctx;
+    int create_status = APC_OK;
+    std::thread creator([&]() {
+        for (uint64_t g = 0; g < n_gpus && create_status == APC_OK; g++)
+            create_status = apc_create((int)(device0 + g), &gpus[g].ctx);
+    });
 
     if (v > 0) print("Parsing FASTA file", tab_level); // :821-825
     Reads seqs;
     {
         std::string err;
-        if (!read_fastx(input_file, seqs, err)) {
+        const bool parsed = read_fastx(input_file, seqs, err);
+        creator.join();
+        if (create_status != APC_OK) return gpu_fail("cannot open CUDA device", nullptr, create_status);
+        if (!parsed) {
             std::cerr << error_pref << err << std::endl;
             return 1;
         }
     }
+    apc_ctx *ctx0 = gpus[0].ctx;
     if (v > 0) print("Number of sequences found: " + std::to_string(seqs.size()) + ".", tab_level);
 
     std::string run_suffix;
@@ -399,6 +405,9 @@ int cli_main(int argc, const char **argv) {
         }
         tab_level--;
     }
+    if (v > 1) print("Releasing the GPU", tab_level);
+    gpus.clear();
+    if (v > 1) print("Exit", tab_level);
     return 0;
 }
 

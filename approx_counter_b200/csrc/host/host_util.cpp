@@ -389,21 +389,23 @@ std::vector<uint8_t> sample_sequences(const Reads &reads, uint64_t nb_sample, ui
     }
     std::shuffle(vec.begin(), vec.end(), g); // :429
     row_len = (uint32_t)(cut + (bot ? 1 : 0));
-    std::vector<uint8_t> sample;
-    sample.reserve((size_t)std::min<uint64_t>(nb_sample, n) * row_len);
-    uint64_t nb_seq = 0, i = 0;
-    while (nb_seq < nb_sample && i < n) { // :447
+    // the walk of :447-471 only needs the read lengths; the copies are done afterwards, in parallel
+    std::vector<uint64_t> chosen;
+    chosen.reserve((size_t)std::min<uint64_t>(nb_sample, n));
+    for (uint64_t i = 0; chosen.size() < nb_sample && i < n; i++) { // :447
         const uint64_t id = (uint64_t)vec[i];
-        const uint64_t len = reads.length(id);
-        if (cut > 0 && len >= cut * 2) { // :461 (current_cut_size == cut_size here)
-            const char *s = reads.seq(id);
-            if (bot) sample.insert(sample.end(), s + (len - 1 - cut), s + len); // suffix(seq, len-1-cut) :463
-            else sample.insert(sample.end(), s, s + cut);                       // prefix(seq, cut) :466
-            nb_seq++;
-        }
-        i++;
+        if (cut > 0 && reads.length(id) >= cut * 2) chosen.push_back(id); // :461 (current_cut_size == cut_size here)
     }
-    n_sampled = nb_seq;
+    n_sampled = chosen.size();
+    std::vector<uint8_t> sample((size_t)n_sampled * row_len);
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < (int64_t)n_sampled; r++) {
+        const uint64_t id = chosen[(size_t)r];
+        const uint64_t len = reads.length(id);
+        const char *s = reads.seq(id);
+        // suffix(seq, len-1-cut) :463 (cut+1 bases) / prefix(seq, cut) :466
+        memcpy(&sample[(size_t)r * row_len], bot ? s + (len - 1 - cut) : s, row_len);
+    }
     return sample;
 }
 
