@@ -149,3 +149,39 @@ def test_sharded_counter_single_rank(built):
     codes, offs = orc.encode_matrix(sample)
     want = orc.error_count(codes, offs, kmers, 16, fast=True)
     assert np.array_equal(got, want) and np.array_equal(got_default, want)
+
+
+def test_planted_adapter_is_recovered(built, tmp_path):
+    """Downstream sanity: a Porechop_ABI-style greedy assembly of the top
+    approximate k-mers rebuilds the adapters planted in the synthetic reads."""
+    from approx_counter_b200 import host
+    k, sl, n = 16, 100, 4000
+    path = tmp_path / "reads.fa"
+    host.synth_write(path, 2024, n, sl)
+    out = tmp_path / "out.txt"
+    p = subprocess.run([BIN, "-k", str(k), "-sn", str(n), "-sl", str(sl), "-lim", "300", "-o", str(out), "-v", "0",
+                        str(path)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    for which, adapter in (("start", "AATGTACTTCGTTCAGTTACGTATTGCT"), ("end", "GCAATACGTAACTGAACGAAGT")):
+        rows = [ln.split("\t") for ln in (tmp_path / f"out.txt_0.{which}").read_text().splitlines()]
+        counts = {a: int(b) for a, b in rows}
+        adapter_kmers = {adapter[i:i + k] for i in range(len(adapter) - k + 1)}
+        top = [a for a, _ in rows[: len(adapter_kmers)]]
+        assert len(set(top) & adapter_kmers) >= 0.8 * len(adapter_kmers), (which, top)
+        # greedy extension from the best k-mer, both directions, while the next k-mer is frequent
+        seq = rows[0][0]
+        floor = counts[seq] * 0.5
+        grown = True
+        while grown:
+            grown = False
+            best = max(((counts.get(seq[-(k - 1):] + c, 0), c) for c in "ACGT"))
+            if best[0] >= floor:
+                seq += best[1]
+                grown = True
+            best = max(((counts.get(c + seq[: k - 1], 0), c) for c in "ACGT"))
+            if best[0] >= floor:
+                seq = best[1] + seq
+                grown = True
+            if len(seq) > 80:
+                break
+        assert adapter in seq or seq in adapter and len(seq) >= len(adapter) - 2, (which, seq)
