@@ -516,13 +516,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="C2")
+    ap.add_argument("--reads", type=int, default=0, help="override the reads per GPU of the workload (C5 sweep)")
+    ap.add_argument("--lim", type=int, default=0, help="override the number of query k-mers (C5 sweep)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="weak: every rank holds its own n-read shard (default); strong: one n-read job split over the ranks")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size, seconds of CPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.reads or args.lim:  # C5: the scaling sweep re-sizes a named workload
+        w["n"] = args.reads or w["n"]
+        w["lim"] = args.lim or w["lim"]
+        w["text"] = f"C5 sweep point on {args.workload}: -sn {w['n']} -sl {w['sl']} -lim {w['lim']}, k={w['k']}"
     if args.impl == "reference":
         return run_reference(args, w)
     return run_b200(args, w)
