@@ -35,7 +35,7 @@ got = s.errorCount(km, k)
 s.close()
 ok = np.array_equal(got, whole)
 codes, offs = orc.encode_matrix(sample[:1500])
-ok = ok and lo % 32 == 0 and (hi - lo) >= n // world - 32
+ok = ok and lo % 32 == 0 and (hi - lo) >= n // world - 32 * world
 flag = torch.tensor([int(ok)], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
