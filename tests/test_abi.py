@@ -73,3 +73,13 @@ def test_sass_is_sm100a(built):
     from approx_counter_b200 import LIB_PATH
     out = subprocess.run(["cuobjdump", "-lelf", LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_reference_shim_compiles_as_cpp14(built, tmp_path):
+    """The header a reference maintainer would include builds without CUDA or SeqAn headers."""
+    libdir = os.path.join(ROOT, "approx_counter_b200", "csrc")
+    subprocess.run(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-I", os.path.join(ROOT, "integration"), os.path.join(ROOT, "integration", "shim_demo.cpp"),
+                    "-o", str(tmp_path / "shim_demo"), "-L", libdir, "-lapc", f"-Wl,-rpath,{libdir}"], check=True)
+    p = subprocess.run([str(tmp_path / "shim_demo")], capture_output=True)
+    assert p.returncode == 2  # usage

@@ -185,3 +185,24 @@ def test_planted_adapter_is_recovered(built, tmp_path):
             if len(seq) > 80:
                 break
         assert adapter in seq or seq in adapter and len(seq) >= len(adapter) - 2, (which, seq)
+
+
+def test_reference_shim(built, tmp_path):
+    """integration/apc_reference_shim.h: the reference's own signatures (count_kmers +
+    get_most_frequent, errorCount) over the C ABI, driven like the reference's main loop."""
+    from approx_counter_b200 import host
+    k, sl, n, lim = 16, 100, 2500, 150
+    path = tmp_path / "reads.fa"
+    host.synth_write(path, 555, n, sl)
+    exe = tmp_path / "shim_demo"
+    libdir = os.path.join(ROOT, "approx_counter_b200", "csrc")
+    subprocess.run(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    "-I", os.path.join(ROOT, "integration"), os.path.join(ROOT, "integration", "shim_demo.cpp"),
+                    "-o", str(exe), "-L", libdir, "-lapc", f"-Wl,-rpath,{libdir}"], check=True)
+    p = subprocess.run([str(exe), str(path), str(k), str(sl), str(lim), "1.0", str(tmp_path / "shim")],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    r = host.Reads(path)
+    want = oracle_files([r.seq(i) for i in range(len(r))], k, sl, lim, 1.0, tmp_path)
+    for which in ("start", "end"):
+        assert (tmp_path / f"shim_0.{which}").read_bytes() == want[which][1]
