@@ -3,6 +3,7 @@
 // only; every CUDA failure becomes a status code plus apc_last_error text.
 #include <algorithm>
 #include <cstring>
+#include <exception>
 #include <new>
 
 #include "apc_internal.h"
@@ -189,7 +190,16 @@ int apc_upload_sample(apc_ctx *c, const uint8_t *bases, uint64_t n_reads, uint32
     return APC_OK;
 }
 
+// no C++ exception may cross the ABI: host containers that fail to allocate become APC_ERR_NOMEM
+#define APC_TRY try {
+#define APC_CATCH(ctx)                                                                   \
+    }                                                                                    \
+    catch (const std::bad_alloc &) { return apc::fail((ctx), APC_ERR_NOMEM, "host allocation failed"); } \
+    catch (const std::exception &e) { return apc::fail((ctx), APC_ERR_INVALID, e.what()); }              \
+    catch (...) { return apc::fail((ctx), APC_ERR_INVALID, "unknown C++ exception"); }
+
 int apc_upload_sample_ragged(apc_ctx *c, const uint8_t *bases, const uint64_t *offsets, uint64_t n_reads) {
+    APC_TRY
     int st = apc::bind(c);
     if (st) return st;
     if (!offsets && n_reads) return apc::fail(c, APC_ERR_INVALID, "offsets is NULL");
@@ -222,6 +232,7 @@ int apc_upload_sample_ragged(apc_ctx *c, const uint8_t *bases, const uint64_t *o
     APC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->timing.upload_ms = apc::elapsed(c->ev[0], c->ev[1]);
     return APC_OK;
+    APC_CATCH(c)
 }
 
 int apc_sample_info(const apc_ctx *c, uint64_t *n_reads, uint32_t *max_len, uint64_t *total_bases) {
@@ -236,6 +247,7 @@ static int exact_common(apc_ctx *c, uint8_t k, float lc, uint64_t lim, uint64_t 
                         const uint64_t *forbidden, uint64_t n_forbidden, uint64_t *kmers_out,
                         uint64_t *counts_out, uint64_t capacity, uint64_t *n_out, uint64_t *n_distinct,
                         uint64_t *n_had_n) {
+    APC_TRY
     int st = apc::bind(c);
     if (st) return st;
     if (k < 2 || k > 32) return apc::fail(c, APC_ERR_INVALID, "k must be in [2,32]");
@@ -255,6 +267,7 @@ static int exact_common(apc_ctx *c, uint8_t k, float lc, uint64_t lim, uint64_t 
     if (!km.empty() && (!kmers_out || !counts_out)) return apc::fail(c, APC_ERR_INVALID, "NULL output");
     for (size_t i = 0; i < km.size(); i++) { kmers_out[i] = km[i]; counts_out[i] = ct[i]; }
     return APC_OK;
+    APC_CATCH(c)
 }
 
 int apc_exact_topn(apc_ctx *c, uint8_t k, float lc_adjusted, uint64_t lim, const uint64_t *forbidden,

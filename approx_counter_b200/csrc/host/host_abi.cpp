@@ -8,13 +8,24 @@
 
 struct apch_reads : public apch::Reads {};
 
+// no C++ exception may cross the C ABI (apch_cli_main excepted: like the reference, an invalid
+// -k / -sl aborts the process through an uncaught std::invalid_argument, :781-787)
+#define APCH_GUARD(fail_value, ...)      \
+    try {                                \
+        __VA_ARGS__                      \
+    } catch (...) {                      \
+        return fail_value;               \
+    }
+
 extern "C" {
 
 int apch_dna2int(const char *seq, uint32_t k, uint64_t *out) {
+    APCH_GUARD(-1,
     uint64_t v = 0;
     if (!seq || !out || !apch::dna2int(seq, k, v)) return -1;
     *out = v;
     return 0;
+    )
 }
 
 void apch_int2dna(uint64_t value, uint32_t k, char *out) {
@@ -32,27 +43,34 @@ int apch_have_low_complexity(uint64_t kmer, uint8_t k, float threshold) {
 uint32_t apch_lc_min_filtered_sum(uint8_t k, float threshold) { return apch::lc_min_filtered_sum(k, threshold); }
 
 uint64_t apch_get_most_frequent(uint64_t *kmers, uint64_t *counts, uint64_t n, uint64_t limit, int k) {
+    APCH_GUARD(0,
     apch::pair_vector v(n);
     for (uint64_t i = 0; i < n; i++) v[i] = {kmers[i], counts[i]};
     apch::get_most_frequent(v, limit, k);
     for (uint64_t i = 0; i < v.size(); i++) { kmers[i] = v[i].first; counts[i] = v[i].second; }
     return v.size();
+    )
 }
 
 int apch_export_counter(const uint64_t *kmers, const uint64_t *counts, uint64_t n, uint8_t k, const char *path) {
+    APCH_GUARD(0,
     apch::pair_vector v(n);
     for (uint64_t i = 0; i < n; i++) v[i] = {kmers[i], counts[i]};
     return apch::export_counter(v, k, path) ? 1 : 0;
+    )
 }
 
 int64_t apch_parse_kmer_list(const char *path, uint64_t *out, uint64_t capacity) {
+    APCH_GUARD(-1,
     std::vector<uint64_t> v;
     if (!apch::parse_kmer_list(path, v)) return -1;
     for (uint64_t i = 0; i < v.size() && i < capacity; i++) out[i] = v[i];
     return (int64_t)v.size();
+    )
 }
 
 int apch_reads_load(const char *path, apch_reads **out) {
+    APCH_GUARD(-1,
     if (!path || !out) return -1;
     apch_reads *r = new (std::nothrow) apch_reads();
     if (!r) return -1;
@@ -64,6 +82,7 @@ int apch_reads_load(const char *path, apch_reads **out) {
     }
     *out = r;
     return 0;
+    )
 }
 uint64_t apch_reads_count(const apch_reads *r) { return r ? r->size() : 0; }
 uint64_t apch_reads_length(const apch_reads *r, uint64_t i) { return r->length(i); }
@@ -72,20 +91,26 @@ void apch_reads_free(apch_reads *r) { delete r; }
 
 int apch_sample(const apch_reads *r, uint64_t nb_sample, uint64_t cut, int bot, int64_t seed, uint8_t *out,
                 uint64_t *n_sampled) {
+    APCH_GUARD(-1,
     if (!r || !n_sampled) return -1;
     uint32_t row = 0;
     const std::vector<uint8_t> s = apch::sample_sequences(*r, nb_sample, cut, bot != 0, seed, *n_sampled, row);
     if (out && !s.empty()) std::memcpy(out, s.data(), s.size());
     return 0;
+    )
 }
 
 int apch_synth_ends(uint64_t seed, uint64_t first, uint64_t n, uint32_t sl, int bot, uint8_t *out) {
+    APCH_GUARD(-1,
     if (!out && n) return -1;
     apch::synth_ends(seed, first, n, sl, bot != 0, out);
     return 0;
+    )
 }
 int apch_synth_write(const char *path, uint64_t seed, uint64_t n, uint32_t sl, int fastq) {
+    APCH_GUARD(-1,
     return path && apch::synth_write(path, seed, n, sl, fastq != 0) ? 0 : -1;
+    )
 }
 
 int apch_cli_main(int argc, const char **argv) { return apch::cli_main(argc, argv); }
