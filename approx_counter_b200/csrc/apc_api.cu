@@ -67,6 +67,11 @@ static int prepare_sample(Ctx *c, uint64_t n_reads, uint32_t max_len, uint64_t t
     const size_t tiles_bytes = ((size_t)c->n_tiles * c->chunks + 1) * kTileReads * sizeof(uint4);
     int st = grow(c, c->d_tiles, c->tiles_bytes, tiles_bytes);
     if (st) return st;
+    // bit planes: 32 tiles per super-group, one uint4 per (column, tile), + two columns of padding
+    // for the kernel's prefetch
+    const size_t n_sg = ((size_t)c->n_tiles + 31) / 32;
+    c->planes_bytes = n_sg * c->chunks * kChunkBases * 32 * sizeof(uint4);
+    if ((st = grow(c, c->d_planes, c->planes_cap, c->planes_bytes + 2 * 32 * sizeof(uint4)))) return st;
     const size_t lens_bytes = ((size_t)c->n_tiles * kTileReads + 1) * sizeof(uint32_t);
     if ((st = grow(c, c->d_lens, c->lens_cap, lens_bytes))) return st;
     APC_CUDA(c, cudaMemsetAsync(c->d_lens, 0, lens_bytes, c->stream));
@@ -136,6 +141,8 @@ void apc_destroy(apc_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_tiles);
     cudaFree(c->d_lens);
+    cudaFree(c->d_planes);
+    cudaFree(c->d_kmers);
     cudaFree(c->d_peq);
     cudaFree(c->d_counts);
     cudaFree(c->d_job_counter);
@@ -177,6 +184,7 @@ int apc_upload_sample_async(apc_ctx *c, const uint8_t *bases, uint64_t n_reads, 
     if (bytes) APC_CUDA(c, cudaMemcpyAsync(c->d_stage, bases, bytes, cudaMemcpyHostToDevice, c->stream));
     APC_CUDA(c, apc::launch_build_tiles_uniform(c->d_stage, n_reads, read_len, c->chunks, c->n_tiles,
                                                 c->d_tiles, c->d_lens, c->stream));
+    APC_CUDA(c, apc::launch_build_planes(*c));
     APC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     c->timing.upload_ms = -1.f; // resolved lazily by apc_last_timing
     return APC_OK;
@@ -228,6 +236,7 @@ int apc_upload_sample_ragged(apc_ctx *c, const uint8_t *bases, const uint64_t *o
     }
     APC_CUDA(c, apc::launch_build_tiles_ragged(c->d_stage, c->d_stage_offs, n_reads, c->chunks, c->n_tiles,
                                                c->d_tiles, c->d_lens, c->stream));
+    APC_CUDA(c, apc::launch_build_planes(*c));
     APC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     APC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->timing.upload_ms = apc::elapsed(c->ev[0], c->ev[1]);
@@ -299,7 +308,9 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
     // the match tables are built in a context-owned pinned buffer so that the H2D copy is
     // truly asynchronous; the buffer is only rewritten once its previous copy has completed
     const uint32_t qg = c->variant.queries_per_group();
-    const size_t table_words = (size_t)((n_kmers + qg - 1) / qg) * apc::kPeqRows * apc::kWordsPerThread;
+    const bool bs = c->variant.bitslice();
+    // row-packed kernels take match tables, the bit-sliced kernel the k-mers themselves
+    const size_t table_words = bs ? (size_t)n_kmers * 2 : (size_t)((n_kmers + qg - 1) / qg) * apc::kPeqRows * apc::kWordsPerThread;
     if (c->table_copy_pending) {
         APC_CUDA(c, cudaEventSynchronize(c->ev_table));
         c->table_copy_pending = false;
@@ -313,12 +324,21 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
         if (e != cudaSuccess) return apc::fail(c, APC_ERR_NOMEM, "cudaMallocHost", e);
         c->pinned_cap = cap;
     }
-    apc::build_peq_tables(kmers, n_kmers, k, c->variant, (uint32_t *)c->h_pinned, c->n_groups);
-    if ((st = apc::grow(c, c->d_peq, c->peq_cap, table_words * sizeof(uint32_t)))) return st;
+    void *d_dst = nullptr;
+    if (bs) {
+        if (n_kmers) std::memcpy(c->h_pinned, kmers, (size_t)n_kmers * sizeof(uint64_t));
+        c->n_groups = n_kmers;
+        if ((st = apc::grow(c, c->d_kmers, c->kmers_cap, table_words * sizeof(uint32_t)))) return st;
+        d_dst = c->d_kmers;
+    } else {
+        apc::build_peq_tables(kmers, n_kmers, k, c->variant, (uint32_t *)c->h_pinned, c->n_groups);
+        if ((st = apc::grow(c, c->d_peq, c->peq_cap, table_words * sizeof(uint32_t)))) return st;
+        d_dst = c->d_peq;
+    }
     const size_t slots = (size_t)c->n_groups * qg;
     if ((st = apc::grow(c, c->d_counts, c->counts_cap, slots * sizeof(unsigned long long)))) return st;
     if (table_words) {
-        APC_CUDA(c, cudaMemcpyAsync(c->d_peq, c->h_pinned, table_words * sizeof(uint32_t), cudaMemcpyHostToDevice,
+        APC_CUDA(c, cudaMemcpyAsync(d_dst, c->h_pinned, table_words * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                     c->stream));
         APC_CUDA(c, cudaEventRecord(c->ev_table, c->stream));
         c->table_copy_pending = true;
@@ -390,8 +410,8 @@ int apc_last_timing(const apc_ctx *cc, apc_timing *out) {
 int apc_set_option(apc_ctx *c, const char *name, int64_t value) {
     if (!c || !name) return APC_ERR_INVALID;
     if (!std::strcmp(name, "scan_variant")) {
-        if (value != 0 && value != 1 && value != 2 && value != 3 && value != 6)
-            return apc::fail(c, APC_ERR_INVALID, "scan_variant must be 0,1,2,3 or 6");
+        if (value != 0 && value != 1 && value != 2 && value != 3 && value != 6 && value != 7 && value != 8)
+            return apc::fail(c, APC_ERR_INVALID, "scan_variant must be 0,1,2,3,6,7 or 8");
         c->opt_variant = (int)value;
         return APC_OK;
     }

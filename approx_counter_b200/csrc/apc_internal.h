@@ -29,10 +29,11 @@ constexpr int kWordsPerThread = 4; // u32 state words per thread = one 16-byte t
 constexpr int kScanWarps = 8;      // warps per CTA of the scan kernel
 
 struct ScanVariant {
-    int nw; // u32 words per unit (1 or 2)
+    int nw; // u32 words per unit (1 or 2); 0 = bit-sliced kernel (bitslice_kernel.cu)
     int f;  // k-mers interleaved per unit
-    int queries_per_group() const { return f * kWordsPerThread / nw; }
-    int rows_per_unit() const { return 32 * nw / f; } // complete k-mer rows a unit can hold
+    bool bitslice() const { return nw == 0; }
+    int queries_per_group() const { return nw ? f * kWordsPerThread / nw : 1; }
+    int rows_per_unit() const { return nw ? 32 * nw / f : 32; } // complete k-mer rows a unit can hold
 };
 
 // device scratch of the exact stage (exact_kernels.cu); grown on demand, kept
@@ -66,6 +67,8 @@ struct Ctx {
     // sample
     uint4 *d_tiles = nullptr;
     size_t tiles_bytes = 0;
+    uint4 *d_planes = nullptr;  // bit planes of the same text (bitslice_kernel.cu), [super-group][column][32 groups]
+    size_t planes_cap = 0, planes_bytes = 0;
     uint32_t *d_lens = nullptr; // per-read length — exact stage
     size_t lens_cap = 0;
     bool has_sample = false;
@@ -81,6 +84,8 @@ struct Ctx {
     uint32_t n_kmers = 0;
     ScanVariant variant{1, 1};
     uint32_t n_groups = 0;
+    uint64_t *d_kmers = nullptr; // the query k-mers themselves (bit-sliced kernel)
+    size_t kmers_cap = 0;
     uint32_t *d_peq = nullptr; // [n_groups][5][4]
     size_t peq_cap = 0;
     unsigned long long *d_counts = nullptr; // [n_groups * queries_per_group]
@@ -132,6 +137,12 @@ ScanVariant pick_variant(int k, int forced);
 void build_peq_tables(const uint64_t *kmers, uint32_t n_kmers, int k, ScanVariant v, uint32_t *table,
                       uint32_t &n_groups);
 cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *launches);
+
+// bitslice_kernel.cu
+cudaError_t launch_build_planes(const Ctx &c);
+cudaError_t launch_bs_scan(const Ctx &c, uint64_t read_lo, uint64_t read_hi, unsigned long long *d_counts,
+                           uint32_t sg_per_job);
+int bs_warps_per_sm(int k);
 
 // exact_kernels.cu
 int exact_count_select(Ctx *c, uint8_t k, float lc_adjusted, uint64_t lim, uint64_t solid_km,

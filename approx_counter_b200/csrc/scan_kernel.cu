@@ -43,12 +43,13 @@ namespace apc {
 
 ScanVariant pick_variant(int k, int forced) {
     ScanVariant v{1, 1};
+    if (forced == 0 || forced == 7) return ScanVariant{0, 1}; // bit-sliced kernel: the default
     switch (forced) {
     case 1: return ScanVariant{1, 1};
     case 2: if (k <= 16) return ScanVariant{1, 2}; break;
     case 3: if (k <= 10) return ScanVariant{1, 3}; break;
     case 6: if (k >= 12 && k <= 21) return ScanVariant{2, 3}; break;
-    default: break;
+    default: break; // 8 (or an unavailable packing): the best row-packed kernel for this k
     }
     if (k <= 10) v = ScanVariant{1, 3};
     else if (k <= 16) v = ScanVariant{1, 2};
@@ -282,6 +283,17 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
     r.tiles = c.d_tiles + (size_t)(first / kTileReads) * c.chunks * kTileReads;
     r.n_tiles = (uint32_t)((count + kTileReads - 1) / kTileReads);
     r.n_reads = count;
+    if (c.variant.bitslice()) {
+        // a job is one k-mer x sg_per_job super-groups (1024 reads each) for one warp
+        uint32_t spj = (uint32_t)c.opt_tiles_per_job;
+        if (spj == 0) {
+            const uint64_t warps = (uint64_t)c.sm_count * bs_warps_per_sm(c.k);
+            const uint64_t jobs1 = ((count + 1023) / 1024) * c.n_kmers;
+            spj = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, jobs1 / (warps * 128)));
+        }
+        *launches = 1;
+        return launch_bs_scan(c, first, first + count, d_counts, spj);
+    }
 
     uint32_t tpj = (uint32_t)c.opt_tiles_per_job;
     if (tpj == 0) {

@@ -143,9 +143,12 @@ uint64_t *apc_counts_device_ptr(apc_ctx *ctx);
 
 int apc_last_timing(const apc_ctx *ctx, apc_timing *out);
 
-/* Tuning / test knobs.  "scan_variant": 0 auto, 1 = one k-mer per 32-bit
- * word, 2 = two per word (k<=16), 3 = three per word (k<=10), 6 = three per
- * 64-bit pair (k<=21).  "tiles_per_job": reads-tiles per CTA (0 auto). */
+/* Tuning / test knobs.  "scan_variant": 0 or 7 = bit-sliced kernel (reads
+ * packed into words, the default), 8 = best row-packed kernel for k, 1 = one
+ * k-mer per 32-bit word, 2 = two per word (k<=16), 3 = three per word
+ * (k<=10), 6 = three per 64-bit pair (k<=21).  "tiles_per_job": work per job
+ * of the persistent warps (0 auto): 32-read tiles for the row-packed
+ * kernels, 1024-read super-groups for the bit-sliced one. */
 int apc_set_option(apc_ctx *ctx, const char *name, int64_t value);
 
 /* Integer-pipe peak microbenchmark (roofline denominator):

@@ -24,6 +24,14 @@ if __name__ == "__main__":
             print(name, "%.4g" % c.microbench(name), flush=True)
         if len(sys.argv) > 1 and sys.argv[1] == "micro":
             sys.exit(0)
+        if len(sys.argv) > 1 and sys.argv[1] == "bs":
+            for args in [(100000, 100, 16, 2000), (100000, 101, 16, 2000), (10000, 100, 16, 500), (200000, 150, 20, 2000),
+                         (200000, 200, 32, 2000), (100000, 100, 10, 2000), (100000, 100, 13, 2000), (200000, 200, 25, 2000)]:
+                for variant in (0, 8):
+                    print(json.dumps(run(c, *args, variant=variant)), flush=True)
+            for tpj in (1, 2, 4, 8):
+                print(json.dumps(run(c, 100000, 100, 16, 2000, 0, tpj)), flush=True)
+            sys.exit(0)
         cases = [(100000, 100, 15, 2000), (100000, 100, 13, 2000), (100000, 100, 9, 2000), (100000, 100, 7, 2000),
                  (200000, 150, 19, 2000), (200000, 150, 18, 2000), (200000, 150, 21, 2000), (200000, 200, 31, 2000), (200000, 200, 29, 2000),(10000, 100, 16, 500), (100000, 100, 16, 2000), (100000, 101, 16, 2000),
                  (100000, 100, 16, 2000, 0, 1), (100000, 100, 16, 2000, 0, 2), (100000, 100, 16, 2000, 0, 4),
