@@ -40,6 +40,10 @@ namespace apc {
 
 constexpr int kGroupsPerSuper = 32; // lanes
 constexpr int bs_warps_per_sm_c(int k) {
+#ifdef APC_BS_MB_OVERRIDE
+    (void)k;
+    return APC_BS_MB_OVERRIDE; // A/B builds (tools/build_ab.sh)
+#endif
     // registers are handed out per SM sub-partition (16384 each), so only multiples of 4 warps matter:
     // 24 -> 80 registers, 20 -> 96, 16 -> 128, 12 -> 168, 8 -> 255
     return k <= 8 ? 24 : k <= 12 ? 20 : k <= 16 ? 16 : k <= 24 ? 12 : 8;

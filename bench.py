@@ -434,9 +434,12 @@ def run_b200(args, w):
         ncu_alu = prof.get(args.workload, {}).get("alu_pipe_pct")
     except Exception:
         pass
-    hbm_bytes_launch = n * (sl + 0.5) + 80 * ((q_start + 7) // 8) + 8 * q_start  # tiles (1 B/base) + tables + counts
+    # bit planes: one uint4 per (32-read group, column), columns padded to 16, groups to 32 per super-group;
+    # + the k-mers and the counts
+    cols_padded = ((sl + 1 + 15) // 16) * 16
+    hbm_bytes_launch = ((n + 1023) // 1024) * 32 * cols_padded * 16 + 16 * q_start
     roofline = {
-        "bound": "int-alu", "kernel": "approx_scan_kernel", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
+        "bound": "int-alu", "kernel": "bs_scan_kernel", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
         "unit": "Tint-op/s", "frac": achieved / alu_peak, "traffic": traffic, "ncu_alu_pipe_pct": ncu_alu,
         "peak_source": f"ALU pipe nominal = {sms} SM x 4 SMSP x 16 lanes/clk x {sm_max:.0f} MHz (SURVEY.md §8d)",
         "algorithmic_ops_per_column": ALGO_OPS_PER_COLUMN, "columns_per_launch": cols_launch,
@@ -446,8 +449,8 @@ def run_b200(args, w):
         "frac_of_measured_lop3_peak": achieved / int_peak["lop3_ops_per_s"],
         "hbm": {"algorithmic_bytes_per_launch": hbm_bytes_launch,
                 "achieved_gbs": hbm_bytes_launch / per_launch_s / 1e9,
-                "peak_gbs": peaks.get("hbm_gbs"), "note": "text is re-read from L2 by every k-mer group; "
-                "the kernel is integer-issue bound, HBM is idle"},
+                "peak_gbs": peaks.get("hbm_gbs"), "note": "the text (bit planes, 0.5 B per base) is re-read from L2 "
+                "by every k-mer; the kernel is bound by the ALU pipe (LOP3), HBM is idle"},
         "sm_mhz_during_run": sm_mhz,
     }
 

@@ -6,7 +6,7 @@ name=$1; shift
 cd "$(dirname "$0")/../approx_counter_b200/csrc"
 mkdir -p ab/$name/host
 ARCH="-gencode arch=compute_100a,code=sm_100a"
-for f in apc_api scan_kernel sample_kernels exact_kernels peak_kernels; do
+for f in apc_api scan_kernel bitslice_kernel sample_kernels exact_kernels peak_kernels; do
   nvcc $ARCH -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -I../../include -I. -Ihost "$@" -c $f.cu -o ab/$name/$f.o &
 done
 wait
