@@ -61,7 +61,9 @@ def log(*a):
 
 
 # ------------------------------------------------------------------------------------------
-# clocks: nvidia-smi sampled DURING the timed region (B200_PROFILING.md "clocks" line)
+# clocks: sampled DURING the timed region (B200_PROFILING.md "clocks" line).  NVML from a thread every
+# few milliseconds when nvidia_ml_py is importable (the timed region of the default run is ~0.2 s, too short
+# for `nvidia-smi -lms`), else the nvidia-smi query of the recipe.
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -69,54 +71,83 @@ class ClockSampler:
     NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, gpu_id):
-        self.rows = []
+        self.rows = []      # (t, sm_mhz, sm_max_mhz, power_w, set(reasons))
         self.proc = None
         self.err = None
+        self.stop_flag = threading.Event()
+        self.source = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByUUID(gpu_id.encode() if isinstance(gpu_id, str) else gpu_id)
+            smax = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = (("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown),
+                    ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown),
+                    ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap))
+
+            def pump():
+                while not self.stop_flag.is_set():
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        self.rows.append((time.perf_counter(), float(sm), float(smax), pw,
+                                          {n for n, b in bits if mask & b}))
+                    except Exception as e:  # keep what we have
+                        self.err = repr(e)
+                        break
+                    time.sleep(0.004)
+
+            self.thread = threading.Thread(target=pump, daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception as e:
+            self.err = repr(e)
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_id), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                  "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread = threading.Thread(target=self._pump_smi, daemon=True)
             self.thread.start()
-        except Exception as e:  # nvidia-smi missing: report, do not invent numbers
+            self.source = "nvidia-smi"
+        except Exception as e:  # neither available: report, do not invent numbers
             self.err = repr(e)
 
-    def _pump(self):
+    def _pump_smi(self):
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
-
-    def mark(self):
-        return time.perf_counter()
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"error": self.err}
-        time.sleep(0.06)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
-        for t, line in self.rows:
-            if t < t0 or t > t1 + 0.06:
-                continue
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
-                power.append(float(parts[2]))
+                row = (time.perf_counter(), float(parts[0]), float(parts[1]), float(parts[2]),
+                       {n for n, v in zip(self.NAMES, parts[3:7]) if v.lower().startswith("active")})
             except ValueError:
                 continue
-            for name, val in zip(self.NAMES, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"error": "no nvidia-smi sample fell inside the timed region", "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
-                "reasons": sorted(reasons), "samples": len(sm)}
+            self.rows.append(row)
+
+    def stop(self, t0, t1):
+        if self.source is None:
+            return {"error": self.err}
+        time.sleep(0.06 if self.source == "nvidia-smi" else 0.01)
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        pad = 0.06 if self.source == "nvidia-smi" else 0.0
+        rows = [r for r in self.rows if t0 <= r[0] <= t1 + pad]
+        if not rows:
+            return {"error": "no clock sample fell inside the timed region", "samples": 0, "source": self.source}
+        reasons = set()
+        for r in rows:
+            reasons |= r[4]
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": max(r[2] for r in rows),
+                "power_w_max": max(r[3] for r in rows), "reasons": sorted(reasons), "samples": len(rows),
+                "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------
