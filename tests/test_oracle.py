@@ -187,3 +187,31 @@ def test_export_format(tmp_path):
     p = tmp_path / "out.txt"
     assert orc.export_counter([orc.dna2int("ACGT"), orc.dna2int("TTTT")], [12, 3], 4, p)
     assert p.read_text() == "ACGT\t12\nTTTT\t3\n"        # :165
+
+
+@pytest.mark.parametrize("n,sl,k,lim,seed,variant", [(3000, 100, 16, 150, 1001, 0), (1500, 150, 20, 120, 1003, 0),
+                                                     (800, 200, 32, 80, 1004, 0), (1500, 100, 16, 100, 1002, 1),
+                                                     (1200, 100, 10, 100, 7, 0)])
+def test_closed_form_equals_seqan_model_on_workloads(built, n, sl, k, lim, seed, variant):
+    """The literal search-scheme recursion against the closed form on the BASELINE workloads themselves
+    (synthetic ONT-like reads, adapters through the error channel, the top-`lim` exact k-mers as queries,
+    both ends): the realistic mix of exact, 1-edit and 2-edit hits, hits cut by the read border, N."""
+    from approx_counter_b200 import host
+    thr = orc.adjust_threshold(1.0, 16, k)
+    for bot in (False, True):
+        sample = host.synth_ends(seed, 0, n, sl, bot)
+        codes, offs = orc.encode_matrix(sample)
+        keys, cnts, _ = orc.count_kmers(codes, offs, k, thr)
+        top, _ = orc.get_most_frequent(keys, cnts, lim, k)
+        rng = np.random.default_rng(seed)
+        extra = np.array([int.from_bytes(rng.bytes(8), "little") & ((1 << (2 * k)) - 1) for _ in range(10)], np.uint64)
+        kmers = np.concatenate([top, extra])
+        want = orc.error_count(codes, offs, kmers, k, fast=True)
+        got, flags = orc.seqan_model_error_count(codes, offs, kmers, k, variant=variant, want_flags=True)
+        assert np.array_equal(got, want)
+        # R0 ⊆ R1 ⊆ R2 per k-mer, and every level is used by the workload
+        assert (flags[:, 0, :] <= flags[:, 1, :]).all() and (flags[:, 1, :] <= flags[:, 2, :]).all()
+        assert flags[:, 0, :].sum() > 0
+        if k <= 20:  # the planted adapters (28 / 22 bases) are shorter than k = 32: only exact hits there
+            assert (flags[:, 1, :] & ~flags[:, 0, :].astype(bool)).sum() > 0
+            assert (flags[:, 2, :] & ~flags[:, 1, :].astype(bool)).sum() > 0
