@@ -177,3 +177,34 @@ def test_async_api_two_contexts(built):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_abi_error_codes(built):
+    """Status codes of the C ABI on a real device: stages out of order, bad arguments."""
+    import ctypes as C
+    from approx_counter_b200 import ApcError, ApproxCounter, load
+    lib = load()
+    assert lib.apc_device_count() >= 1
+    h = C.c_void_p()
+    assert lib.apc_create(10 ** 6, C.byref(h)) == -3                     # APC_ERR_NO_DEVICE
+    with ApproxCounter(0) as c:
+        with pytest.raises(ApcError, match="NO_SAMPLE"):
+            c.errorCount([1, 2], 8)                                      # scan before upload
+        with pytest.raises(ApcError, match="NO_SAMPLE"):
+            c.count_kmers_topn(8, 1.0, 5)
+        c.upload_sample(np.full((4, 20), ord("A"), np.uint8))
+        with pytest.raises(ApcError, match="NO_QUERIES"):
+            c.scan()                                                     # scan before set_queries
+        with pytest.raises(ApcError, match="INVALID"):
+            c.errorCount([1], 1)                                         # k < 2 (:781)
+        with pytest.raises(ApcError, match="INVALID"):
+            c.errorCount([1], 33)                                        # k > 32
+        with pytest.raises(ApcError, match="INVALID"):
+            c.errorCount([1 << 16], 8)                                   # value wider than 2k bits
+        with pytest.raises(ApcError, match="INVALID"):
+            c.set_option("no_such_option", 1)
+        with pytest.raises(ApcError, match="INVALID"):
+            c.set_option("scan_variant", 5)
+        assert c.errorCount([0], 8).tolist() == [3 * 4]                  # still usable after the errors: AAAAAAAA
+        n, ml, tb = c.sample_info()
+        assert (n, ml, tb) == (4, 20, 80)
