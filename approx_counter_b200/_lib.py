@@ -51,6 +51,7 @@ SYMBOLS = {
     "apc_scan": (C.c_int, [_vp, _vp]),
     "apc_get_counts": (C.c_int, [_vp, _vp]),
     "apc_counts_device_ptr": (_vp, [_vp]),
+    "apc_last_scan_launches": (C.c_uint64, [_vp]),
     "apc_last_timing": (C.c_int, [_vp, C.POINTER(ApcTiming)]),
     "apc_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "apc_measure_int_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double),

@@ -175,6 +175,10 @@ class ApproxCounter:
                 "total_ms": t.total_ms, "scan_launches": int(t.scan_launches),
                 "exact_launches": int(t.exact_launches)}
 
+    def timing_launches(self):
+        """Kernels launched by the last scan (no synchronisation)."""
+        return int(self._lib.apc_last_scan_launches(self._h))
+
     def measure_int_peak(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self._check(self._lib.apc_measure_int_peak(self._h, C.byref(a), C.byref(b), C.byref(c)))

@@ -310,7 +310,7 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
     const uint32_t qg = c->variant.queries_per_group();
     const bool bs = c->variant.bitslice();
     // row-packed kernels take match tables, the bit-sliced kernel the k-mers themselves
-    const size_t table_words = bs ? (size_t)n_kmers * 2 : (size_t)((n_kmers + qg - 1) / qg) * apc::kPeqRows * apc::kWordsPerThread;
+    const size_t table_words = bs ? (size_t)n_kmers * 3 : (size_t)((n_kmers + qg - 1) / qg) * apc::kPeqRows * apc::kWordsPerThread;
     if (c->table_copy_pending) {
         APC_CUDA(c, cudaEventSynchronize(c->ev_table));
         c->table_copy_pending = false;
@@ -326,7 +326,15 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
     }
     void *d_dst = nullptr;
     if (bs) {
-        if (n_kmers) std::memcpy(c->h_pinned, kmers, (size_t)n_kmers * sizeof(uint64_t));
+        // k-mers in scan order (pairs with a common prefix first), then the index of each in the caller's order
+        std::vector<uint32_t> order;
+        c->n_pairs = apc::bs_pair_queries(kmers, n_kmers, k, c->variant.pairing(), order);
+        uint64_t *hk = (uint64_t *)c->h_pinned;
+        uint32_t *hp = (uint32_t *)(hk + n_kmers);
+        for (uint32_t i = 0; i < n_kmers; i++) {
+            hk[i] = kmers[order[i]];
+            hp[i] = order[i];
+        }
         c->n_groups = n_kmers;
         if ((st = apc::grow(c, c->d_kmers, c->kmers_cap, table_words * sizeof(uint32_t)))) return st;
         d_dst = c->d_kmers;
@@ -396,6 +404,8 @@ int apc_approx_count(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_km
     c->timing.total_ms = apc::elapsed(c->ev[4], c->ev[5]);
     return APC_OK;
 }
+
+uint64_t apc_last_scan_launches(const apc_ctx *c) { return c ? c->timing.scan_launches : 0; }
 
 int apc_last_timing(const apc_ctx *cc, apc_timing *out) {
     apc_ctx *c = const_cast<apc_ctx *>(cc);

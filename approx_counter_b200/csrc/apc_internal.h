@@ -32,6 +32,7 @@ struct ScanVariant {
     int nw; // u32 words per unit (1 or 2); 0 = bit-sliced kernel (bitslice_kernel.cu)
     int f;  // k-mers interleaved per unit
     bool bitslice() const { return nw == 0; }
+    bool pairing() const { return nw == 0 && f == 1; } // f == 0: bit-sliced without k-mer pairing (scan_variant 7)
     int queries_per_group() const { return nw ? f * kWordsPerThread / nw : 1; }
     int rows_per_unit() const { return nw ? 32 * nw / f : 32; } // complete k-mer rows a unit can hold
 };
@@ -84,7 +85,8 @@ struct Ctx {
     uint32_t n_kmers = 0;
     ScanVariant variant{1, 1};
     uint32_t n_groups = 0;
-    uint64_t *d_kmers = nullptr; // the query k-mers themselves (bit-sliced kernel)
+    uint64_t *d_kmers = nullptr; // bit-sliced kernel: the query k-mers (pair members first), then u32 perm[n]
+    uint32_t n_pairs = 0;        // pairs of k-mers with a common prefix >= k/2 (bs_pair_kernel)
     size_t kmers_cap = 0;
     uint32_t *d_peq = nullptr; // [n_groups][5][4]
     size_t peq_cap = 0;
@@ -141,7 +143,8 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
 // bitslice_kernel.cu
 cudaError_t launch_build_planes(const Ctx &c);
 cudaError_t launch_bs_scan(const Ctx &c, uint64_t read_lo, uint64_t read_hi, unsigned long long *d_counts,
-                           uint32_t sg_per_job);
+                           uint32_t sg_per_job, uint64_t *launches);
+uint32_t bs_pair_queries(const uint64_t *kmers, uint32_t n, int k, bool enable, std::vector<uint32_t> &order);
 int bs_warps_per_sm(int k);
 
 // exact_kernels.cu

@@ -85,37 +85,84 @@ cudaError_t launch_build_planes(const Ctx &c) {
 }
 
 // ---- K1 (bit-sliced) --------------------------------------------------------------------------
-template <int K>
-struct BsState {
-    uint32_t r0[K], r1[K], r2[K];
+// Values handed from row i-1 to row i inside one column.
+struct BsCarry {
+    uint32_t p0, p1, p2; // previous column's row i-1, levels 0..2 (row -1 = empty prefix: always matches)
+    uint32_t n0p, n1p;   // this column's row i-1, levels 0 and 1
 };
 
-// one text column: e_i from the warp's mask slot, then the K rows
-template <int K>
-__device__ __forceinline__ void bs_column(BsState<K> &st, const char *slot_lane, const uint32_t (&off)[K]) {
+__device__ __forceinline__ BsCarry bs_carry_init() {
     const uint32_t ALL = 0xFFFFFFFFu;
-    uint32_t p0 = ALL, p1 = ALL, p2 = ALL; // previous column's row i-1 (row -1 = empty prefix: always matches)
-    uint32_t n0p = ALL, n1p = ALL;         // this column's row i-1, levels 0 and 1
+    return BsCarry{ALL, ALL, ALL, ALL, ALL};
+}
+
+// N consecutive rows of one text column, the first of them being row FIRST of the k-mer: e_i
+// from the warp's mask slot (LDS with a uniform-register offset), then the five LOP3 of the row.
+template <int N, int FIRST>
+__device__ __forceinline__ void bs_rows(uint32_t (&r0)[N], uint32_t (&r1)[N], uint32_t (&r2)[N], BsCarry &c,
+                                        const char *slot_lane, const uint32_t (&off)[N]) {
+    const uint32_t ALL = 0xFFFFFFFFu;
 #pragma unroll
-    for (int i = 0; i < K; i++) {
-        const uint32_t e = *reinterpret_cast<const uint32_t *>(slot_lane + off[i]);
-        const uint32_t o0 = st.r0[i], o1 = st.r1[i], o2 = st.r2[i];
-        const uint32_t n0 = i < 1 ? e : and2(p0, e);
+    for (int j = 0; j < N; j++) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int i = FIRST + j;
+        const uint32_t e = *reinterpret_cast<const uint32_t *>(slot_lane + off[j]);
+        const uint32_t o0 = r0[j], o1 = r1[j], o2 = r2[j];
+        const uint32_t n0 = i < 1 ? e : and2(c.p0, e);
         // rows 0 (level 1) and 0..1 (level 2) always match: that many k-mer bases can be skipped
-        const uint32_t n1 = i < 1 ? ALL : or3(and_or(p1, e, o0), p0, n0p);
-        const uint32_t n2 = i < 2 ? ALL : or3(and_or(p2, e, o1), p1, n1p);
-        st.r0[i] = n0; st.r1[i] = n1; st.r2[i] = n2;
-        p0 = o0; p1 = o1; p2 = o2;
-        n0p = n0; n1p = n1;
+        const uint32_t n1 = i < 1 ? ALL : or3(and_or(c.p1, e, o0), c.p0, c.n0p);
+        const uint32_t n2 = i < 2 ? ALL : or3(and_or(c.p2, e, o1), c.p1, c.n1p);
+        r0[j] = n0; r1[j] = n1; r2[j] = n2;
+        c.p0 = o0; c.p1 = o1; c.p2 = o2;
+        c.n0p = n0; c.n1p = n1;
     }
 }
 
+template <int N, int FIRST>
+__device__ __forceinline__ void bs_rows_init(uint32_t (&r0)[N], uint32_t (&r1)[N], uint32_t (&r2)[N]) {
+    const uint32_t ALL = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        r0[j] = 0;
+        r1[j] = FIRST + j < 1 ? ALL : 0; // prefix 1 by one deletion
+        r2[j] = FIRST + j < 2 ? ALL : 0; // prefixes 1..2 by deletions
+    }
+}
+
+// mask of the reads of group (sg, lane) that lie inside the scanned range
+__device__ __forceinline__ uint32_t bs_valid_mask(uint64_t first, uint64_t range_lo, uint64_t range_hi) {
+    const uint32_t ALL = 0xFFFFFFFFu;
+    uint32_t vm = 0;
+    if (first < range_hi && first + 32 > range_lo) {
+        vm = ALL;
+        if (range_lo > first) vm &= ALL << (uint32_t)(range_lo - first);
+        if (range_hi < first + 32) vm &= ALL >> (uint32_t)(first + 32 - range_hi);
+    }
+    return vm;
+}
+
+// job fetch of the persistent warps: warp-uniform result (ptxas keeps it in uniform registers)
+__device__ __forceinline__ uint32_t bs_next_job(unsigned int *job_counter, uint32_t n_jobs, uint32_t lane) {
+    uint32_t job = 0;
+    if (lane == 0) {
+        job = atomicAdd(job_counter, 1u);
+        if (job == n_jobs + gridDim.x - 1u) atomicExch(job_counter, 0u); // last fetch of the launch re-arms the queue
+    }
+    return __shfl_sync(0xFFFFFFFFu, job, 0);
+}
+
+#define APC_BS_STAGE_MASKS()                                                                                          \
+    s_mask[0][lane] = ma.x; s_mask[0][32 + lane] = ma.y; s_mask[0][64 + lane] = ma.z; s_mask[0][96 + lane] = ma.w;   \
+    s_mask[1][lane] = mb.x; s_mask[1][32 + lane] = mb.y; s_mask[1][64 + lane] = mb.z; s_mask[1][96 + lane] = mb.w;
+
+// One k-mer per warp.  kmers[q0 + u] is the k-mer of unit u, perm[q0 + u] its index in the caller's order.
 template <int K, int MB>
 __global__ void __launch_bounds__(32, MB)
 bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const uint32_t n_sg, const uint32_t cols,
                const uint32_t read_len, const uint64_t range_lo, const uint64_t range_hi,
-               const uint64_t *__restrict__ kmers, const uint32_t n_kmers, const uint32_t sg_per_job,
-               const uint32_t n_jobs, unsigned long long *__restrict__ counts,
+               const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ perm, const uint32_t n_units,
+               const uint32_t sg_per_job, const uint32_t n_jobs, unsigned long long *__restrict__ counts,
                unsigned int *__restrict__ job_counter) {
     __shared__ __align__(16) uint32_t s_mask[2][4 * kGroupsPerSuper];
     const uint32_t lane = threadIdx.x;
@@ -123,15 +170,10 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
     const uint32_t pairs = (read_len + 1) / 2; // an odd length is rounded up with one padding column (N: matches nothing)
 
     for (;;) {
-        uint32_t job = 0;
-        if (lane == 0) {
-            job = atomicAdd(job_counter, 1u);
-            if (job == n_jobs + gridDim.x - 1u) atomicExch(job_counter, 0u); // last fetch of the launch re-arms the queue
-        }
-        job = __shfl_sync(0xFFFFFFFFu, job, 0); // warp-uniform from here on (ptxas keeps it in uniform registers)
+        const uint32_t job = bs_next_job(job_counter, n_jobs, lane);
         if (job >= n_jobs) break;
-        const uint32_t q = job % n_kmers, jb = job / n_kmers;
-        const uint64_t kmer = __ldg(kmers + q);
+        const uint32_t u = job % n_units, jb = job / n_units;
+        const uint64_t kmer = __ldg(kmers + u);
         uint32_t off[K]; // byte offset of the mask row (A, C, G, T) that k-mer base i selects
 #pragma unroll
         for (int i = 0; i < K; i++) off[i] = (uint32_t)((kmer >> (2 * (K - 1 - i))) & 3u) * kPlaneRow;
@@ -139,68 +181,190 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
         uint32_t cnt = 0;
         const uint32_t sg_end = min(n_sg, (jb + 1) * sg_per_job);
         for (uint32_t sg = jb * sg_per_job; sg < sg_end; sg++) {
-            BsState<K> st;
-#pragma unroll
-            for (int i = 0; i < K; i++) {
-                st.r0[i] = 0;
-                st.r1[i] = i < 1 ? ALL : 0; // prefix 1 by one deletion
-                st.r2[i] = i < 2 ? ALL : 0; // prefixes 1..2 by deletions
-            }
+            uint32_t r0[K], r1[K], r2[K];
+            bs_rows_init<K, 0>(r0, r1, r2);
             uint32_t a0 = 0, a1 = K <= 1 ? ALL : 0, a2 = K <= 2 ? ALL : 0;
             const uint4 *p = planes + ((size_t)(sg_first + sg) * cols) * kGroupsPerSuper + lane;
             uint4 ma = __ldg(p), mb = __ldg(p + kGroupsPerSuper);
             for (uint32_t pr = 0; pr < pairs; pr++) {
                 p += 2 * kGroupsPerSuper;
                 const uint4 na = __ldg(p), nb = __ldg(p + kGroupsPerSuper); // buffer is padded by two columns
-                s_mask[0][lane] = ma.x; s_mask[0][32 + lane] = ma.y; s_mask[0][64 + lane] = ma.z; s_mask[0][96 + lane] = ma.w;
-                s_mask[1][lane] = mb.x; s_mask[1][32 + lane] = mb.y; s_mask[1][64 + lane] = mb.z; s_mask[1][96 + lane] = mb.w;
-                bs_column<K>(st, reinterpret_cast<const char *>(s_mask[0]) + lane * 4, off);
-                const uint32_t h0 = st.r0[K - 1], h1 = st.r1[K - 1], h2 = st.r2[K - 1];
-                bs_column<K>(st, reinterpret_cast<const char *>(s_mask[1]) + lane * 4, off);
-                a0 = or3(a0, h0, st.r0[K - 1]);
-                a1 = or3(a1, h1, st.r1[K - 1]);
-                a2 = or3(a2, h2, st.r2[K - 1]);
+                APC_BS_STAGE_MASKS()
+                BsCarry c = bs_carry_init();
+                bs_rows<K, 0>(r0, r1, r2, c, reinterpret_cast<const char *>(s_mask[0]) + lane * 4, off);
+                const uint32_t h0 = r0[K - 1], h1 = r1[K - 1], h2 = r2[K - 1];
+                c = bs_carry_init();
+                bs_rows<K, 0>(r0, r1, r2, c, reinterpret_cast<const char *>(s_mask[1]) + lane * 4, off);
+                a0 = or3(a0, h0, r0[K - 1]);
+                a1 = or3(a1, h1, r1[K - 1]);
+                a2 = or3(a2, h2, r2[K - 1]);
                 ma = na; mb = nb;
             }
             // hits of these 32 reads: [d<=0] + [d<=1] + [d<=2] (:589-593), reads outside the
             // scanned range (padding of the last group, or a sub-range scan) masked out
-            const uint64_t first = ((uint64_t)(sg_first + sg) * kGroupsPerSuper + lane) * 32;
-            uint32_t vm = 0;
-            if (first < range_hi && first + 32 > range_lo) {
-                vm = ALL;
-                if (range_lo > first) vm &= ALL << (uint32_t)(range_lo - first);
-                if (range_hi < first + 32) vm &= ALL >> (uint32_t)(first + 32 - range_hi);
-            }
+            const uint32_t vm = bs_valid_mask(((uint64_t)(sg_first + sg) * kGroupsPerSuper + lane) * 32, range_lo, range_hi);
             cnt += __popc(a0 & vm) + __popc(a1 & vm) + __popc(a2 & vm);
         }
         const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, cnt);
-        if (lane == 0 && total) atomicAdd(&counts[q], (unsigned long long)total);
+        if (lane == 0 && total) atomicAdd(&counts[__ldg(perm + u)], (unsigned long long)total);
     }
 }
 
+// Two k-mers with a common prefix of at least P bases per warp.  Rows 0..P-1 of their tables
+// are identical in every column, so they are computed once: 5(2K - P) instead of 10K LOP3 per
+// column.  The query k-mers of the reference's pipeline are the most frequent k-mers of the
+// sample, i.e. mostly an adapter's windows and their one-error variants, which share long
+// prefixes once sorted (C2: two thirds of the 2000 k-mers pair up at P = 8).
+template <int K, int P, int MB>
+__global__ void __launch_bounds__(32, MB)
+bs_pair_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const uint32_t n_sg, const uint32_t cols,
+               const uint32_t read_len, const uint64_t range_lo, const uint64_t range_hi,
+               const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ perm, const uint32_t n_units,
+               const uint32_t sg_per_job, const uint32_t n_jobs, unsigned long long *__restrict__ counts,
+               unsigned int *__restrict__ job_counter) {
+    constexpr int T = K - P; // rows of the private tails
+    static_assert(P >= 2 && T >= 1, "the always-matching rows 0..1 must lie in the shared part");
+    __shared__ __align__(16) uint32_t s_mask[2][4 * kGroupsPerSuper];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t pairs = (read_len + 1) / 2;
+
+    for (;;) {
+        const uint32_t job = bs_next_job(job_counter, n_jobs, lane);
+        if (job >= n_jobs) break;
+        const uint32_t u = job % n_units, jb = job / n_units;
+        const uint64_t ka = __ldg(kmers + 2 * u), kb = __ldg(kmers + 2 * u + 1);
+        uint32_t off_s[P], off_a[T], off_b[T];
+#pragma unroll
+        for (int i = 0; i < P; i++) off_s[i] = (uint32_t)((ka >> (2 * (K - 1 - i))) & 3u) * kPlaneRow;
+#pragma unroll
+        for (int i = 0; i < T; i++) {
+            off_a[i] = (uint32_t)((ka >> (2 * (T - 1 - i))) & 3u) * kPlaneRow;
+            off_b[i] = (uint32_t)((kb >> (2 * (T - 1 - i))) & 3u) * kPlaneRow;
+        }
+        uint32_t cnt_a = 0, cnt_b = 0;
+        const uint32_t sg_end = min(n_sg, (jb + 1) * sg_per_job);
+        for (uint32_t sg = jb * sg_per_job; sg < sg_end; sg++) {
+            uint32_t s0[P], s1[P], s2[P], x0[T], x1[T], x2[T], y0[T], y1[T], y2[T];
+            bs_rows_init<P, 0>(s0, s1, s2);
+            bs_rows_init<T, P>(x0, x1, x2);
+            bs_rows_init<T, P>(y0, y1, y2);
+            uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+            const uint4 *p = planes + ((size_t)(sg_first + sg) * cols) * kGroupsPerSuper + lane;
+            uint4 ma = __ldg(p), mb = __ldg(p + kGroupsPerSuper);
+            for (uint32_t pr = 0; pr < pairs; pr++) {
+                p += 2 * kGroupsPerSuper;
+                const uint4 na = __ldg(p), nb = __ldg(p + kGroupsPerSuper);
+                APC_BS_STAGE_MASKS()
+                uint32_t ha[3], hb[3];
+#pragma unroll
+                for (int col = 0; col < 2; col++) {
+                    const char *slot = reinterpret_cast<const char *>(s_mask[col]) + lane * 4;
+                    BsCarry c = bs_carry_init();
+                    bs_rows<P, 0>(s0, s1, s2, c, slot, off_s);
+                    BsCarry cb = c;
+                    bs_rows<T, P>(x0, x1, x2, c, slot, off_a);
+                    bs_rows<T, P>(y0, y1, y2, cb, slot, off_b);
+                    if (col == 0) {
+                        ha[0] = x0[T - 1]; ha[1] = x1[T - 1]; ha[2] = x2[T - 1];
+                        hb[0] = y0[T - 1]; hb[1] = y1[T - 1]; hb[2] = y2[T - 1];
+                    }
+                }
+                a0 = or3(a0, ha[0], x0[T - 1]); a1 = or3(a1, ha[1], x1[T - 1]); a2 = or3(a2, ha[2], x2[T - 1]);
+                b0 = or3(b0, hb[0], y0[T - 1]); b1 = or3(b1, hb[1], y1[T - 1]); b2 = or3(b2, hb[2], y2[T - 1]);
+                ma = na; mb = nb;
+            }
+            const uint32_t vm = bs_valid_mask(((uint64_t)(sg_first + sg) * kGroupsPerSuper + lane) * 32, range_lo, range_hi);
+            cnt_a += __popc(a0 & vm) + __popc(a1 & vm) + __popc(a2 & vm);
+            cnt_b += __popc(b0 & vm) + __popc(b1 & vm) + __popc(b2 & vm);
+        }
+        const uint32_t ta = __reduce_add_sync(0xFFFFFFFFu, cnt_a), tb = __reduce_add_sync(0xFFFFFFFFu, cnt_b);
+        if (lane == 0 && ta) atomicAdd(&counts[__ldg(perm + 2 * u)], (unsigned long long)ta);
+        if (lane == 0 && tb) atomicAdd(&counts[__ldg(perm + 2 * u + 1)], (unsigned long long)tb);
+    }
+}
+
+struct BsRange {
+    uint32_t sg_first, n_sg;
+    uint64_t lo, hi;
+};
+
 template <int K>
-static cudaError_t launch_bs_k(const Ctx &c, uint64_t lo, uint64_t hi, unsigned long long *d_counts, uint32_t sg_per_job) {
-    // registers: 3K of state + the row masks of two columns in flight (ptxas wants about 6K + 26);
-    // CTAs (= warps) per SM chosen so that nothing spills
-    constexpr int MB = bs_warps_per_sm_c(K);
-    const uint32_t sg_first = (uint32_t)(lo / (32 * kGroupsPerSuper));
-    const uint32_t sg_last = (uint32_t)((hi + 32 * kGroupsPerSuper - 1) / (32 * kGroupsPerSuper));
-    const uint32_t n_sg = sg_last - sg_first;
-    const uint64_t jobs = (uint64_t)((n_sg + sg_per_job - 1) / sg_per_job) * c.n_kmers;
-    if (jobs == 0) return cudaSuccess;
-    if (jobs > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
-    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c.sm_count * MB, jobs);
-    bs_scan_kernel<K, MB><<<grid, 32, 0, c.stream>>>(c.d_planes, sg_first, n_sg, c.chunks * kChunkBases, c.max_len, lo, hi,
-                                                     c.d_kmers, c.n_kmers, sg_per_job, (uint32_t)jobs, d_counts,
-                                                     c.d_job_counter);
-    return cudaGetLastError();
+static cudaError_t launch_bs_k(const Ctx &c, const BsRange &r, unsigned long long *d_counts, uint32_t sg_per_job,
+                               uint64_t *launches) {
+    const uint32_t sg_blocks = (r.n_sg + sg_per_job - 1) / sg_per_job;
+    const uint32_t cols = c.chunks * kChunkBases;
+    const uint32_t *perm = reinterpret_cast<const uint32_t *>(c.d_kmers + c.n_kmers);
+    // pairs first (the longer jobs), then the k-mers that found no partner
+    if constexpr (K >= 4) if (c.n_pairs) {
+        constexpr int P = K / 2;
+        constexpr int MB = bs_warps_per_sm_c(2 * K - P);
+        const uint64_t jobs = (uint64_t)sg_blocks * c.n_pairs;
+        if (jobs > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c.sm_count * MB, jobs);
+        bs_pair_kernel<K, P, MB><<<grid, 32, 0, c.stream>>>(c.d_planes, r.sg_first, r.n_sg, cols, c.max_len, r.lo, r.hi,
+                                                            c.d_kmers, perm, c.n_pairs, sg_per_job, (uint32_t)jobs,
+                                                            d_counts, c.d_job_counter);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        (*launches)++;
+    }
+    const uint32_t n_single = c.n_kmers - 2 * c.n_pairs;
+    if (n_single) {
+        // registers: 3K of state + the row masks of two columns in flight (ptxas wants about 6K + 26);
+        // CTAs (= warps) per SM chosen so that nothing spills
+        constexpr int MB = bs_warps_per_sm_c(K);
+        const uint64_t jobs = (uint64_t)sg_blocks * n_single;
+        if (jobs > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c.sm_count * MB, jobs);
+        bs_scan_kernel<K, MB><<<grid, 32, 0, c.stream>>>(c.d_planes, r.sg_first, r.n_sg, cols, c.max_len, r.lo, r.hi,
+                                                         c.d_kmers + 2 * c.n_pairs, perm + 2 * c.n_pairs, n_single,
+                                                         sg_per_job, (uint32_t)jobs, d_counts, c.d_job_counter);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        (*launches)++;
+    }
+    return cudaSuccess;
 }
 
 int bs_warps_per_sm(int k) { return bs_warps_per_sm_c(k); }
 
-cudaError_t launch_bs_scan(const Ctx &c, uint64_t lo, uint64_t hi, unsigned long long *d_counts, uint32_t sg_per_job) {
+// Host side of the pairing: sort the k-mers, pair neighbours whose common prefix is at least
+// k/2 bases.  order[] receives the k-mer indices, the 2*n_pairs pair members first.
+uint32_t bs_pair_queries(const uint64_t *kmers, uint32_t n, int k, bool enable, std::vector<uint32_t> &order) {
+    order.resize(n);
+    for (uint32_t i = 0; i < n; i++) order[i] = i;
+    if (!enable || k < 4 || n < 2) return 0;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return kmers[a] != kmers[b] ? kmers[a] < kmers[b] : a < b; });
+    const int p = k / 2;
+    std::vector<uint32_t> pairs, singles;
+    pairs.reserve(n);
+    for (uint32_t i = 0; i < n;) {
+        if (i + 1 < n && ((kmers[order[i]] ^ kmers[order[i + 1]]) >> (2 * (k - p))) == 0) {
+            pairs.push_back(order[i]);
+            pairs.push_back(order[i + 1]);
+            i += 2;
+        } else {
+            singles.push_back(order[i]);
+            i += 1;
+        }
+    }
+    const uint32_t n_pairs = (uint32_t)(pairs.size() / 2);
+    std::copy(pairs.begin(), pairs.end(), order.begin());
+    std::copy(singles.begin(), singles.end(), order.begin() + pairs.size());
+    return n_pairs;
+}
+
+cudaError_t launch_bs_scan(const Ctx &c, uint64_t lo, uint64_t hi, unsigned long long *d_counts, uint32_t sg_per_job,
+                           uint64_t *launches) {
+    BsRange r;
+    r.lo = lo;
+    r.hi = hi;
+    r.sg_first = (uint32_t)(lo / (32 * kGroupsPerSuper));
+    r.n_sg = (uint32_t)((hi + 32 * kGroupsPerSuper - 1) / (32 * kGroupsPerSuper)) - r.sg_first;
+    *launches = 0;
+    if (r.n_sg == 0 || c.n_kmers == 0) return cudaSuccess;
     switch (c.k) {
-#define APC_BS_CASE(K_) case K_: return launch_bs_k<K_>(c, lo, hi, d_counts, sg_per_job);
+#define APC_BS_CASE(K_) case K_: return launch_bs_k<K_>(c, r, d_counts, sg_per_job, launches);
         APC_BS_CASE(2) APC_BS_CASE(3) APC_BS_CASE(4) APC_BS_CASE(5) APC_BS_CASE(6) APC_BS_CASE(7) APC_BS_CASE(8)
         APC_BS_CASE(9) APC_BS_CASE(10) APC_BS_CASE(11) APC_BS_CASE(12) APC_BS_CASE(13) APC_BS_CASE(14)
         APC_BS_CASE(15) APC_BS_CASE(16) APC_BS_CASE(17) APC_BS_CASE(18) APC_BS_CASE(19) APC_BS_CASE(20)

@@ -43,7 +43,8 @@ namespace apc {
 
 ScanVariant pick_variant(int k, int forced) {
     ScanVariant v{1, 1};
-    if (forced == 0 || forced == 7) return ScanVariant{0, 1}; // bit-sliced kernel: the default
+    if (forced == 0) return ScanVariant{0, 1}; // bit-sliced kernel with k-mer pairing: the default
+    if (forced == 7) return ScanVariant{0, 0}; // bit-sliced kernel, every k-mer on its own
     switch (forced) {
     case 1: return ScanVariant{1, 1};
     case 2: if (k <= 16) return ScanVariant{1, 2}; break;
@@ -291,8 +292,7 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
             const uint64_t jobs1 = ((count + 1023) / 1024) * c.n_kmers;
             spj = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, jobs1 / (warps * 128)));
         }
-        *launches = 1;
-        return launch_bs_scan(c, first, first + count, d_counts, spj);
+        return launch_bs_scan(c, first, first + count, d_counts, spj, launches);
     }
 
     uint32_t tpj = (uint32_t)c.opt_tiles_per_job;

@@ -308,6 +308,7 @@ def run_b200(args, w):
     ends = (h_start, h_end)
     ctxs = [ApproxCounter(local_rank), ApproxCounter(local_rank)]
     for c, s in zip(ctxs, ends):
+        c.set_option("scan_variant", args.scan_variant)
         c.set_stream(stream.cuda_stream)
         c.upload_sample_ptr(s.ctypes.data, s.shape[0], s.shape[1])
 
@@ -345,7 +346,7 @@ def run_b200(args, w):
             if record:
                 e1.record(stream)
                 kernel_events.append((e0, e1))
-            launches[0] += 1
+            launches[0] += c.timing_launches()
             allreduce_counts(out)
 
     def barrier():
@@ -450,7 +451,9 @@ def run_b200(args, w):
     sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     alu_peak = sms * 4 * 16 * sm_max * 1e6  # ALU pipe: 16 lanes/clk/SMSP (B300_MICROARCH.md:85)
-    per_launch_s = kern_ms / 1e3 / max(n_launch, 1)
+    # a scan is one or two launches (k-mer pairs, then the unpaired k-mers): the roofline unit is the scan
+    n_scans = max(len(kernel_events), 1)
+    per_launch_s = kern_ms / 1e3 / n_scans
     cols_launch = cols_rank / 2.0
     # no kernel can retire more than one instruction per SMSP per clock; a faster reading means
     # the event pairs did not contain the kernel (e.g. it ran on another stream)
@@ -470,11 +473,11 @@ def run_b200(args, w):
     cols_padded = ((sl + 1 + 15) // 16) * 16
     hbm_bytes_launch = ((n + 1023) // 1024) * 32 * cols_padded * 16 + 16 * q_start
     roofline = {
-        "bound": "int-alu", "kernel": "bs_scan_kernel", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
+        "bound": "int-alu", "kernel": "bs_pair_kernel + bs_scan_kernel (one scan)", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
         "unit": "Tint-op/s", "frac": achieved / alu_peak, "traffic": traffic, "ncu_alu_pipe_pct": ncu_alu,
         "peak_source": f"ALU pipe nominal = {sms} SM x 4 SMSP x 16 lanes/clk x {sm_max:.0f} MHz (SURVEY.md §8d)",
         "algorithmic_ops_per_column": ALGO_OPS_PER_COLUMN, "columns_per_launch": cols_launch,
-        "avg_launch_ms": per_launch_s * 1e3, "launches_timed": n_launch,
+        "avg_launch_ms": per_launch_s * 1e3, "scans_timed": n_scans, "launches_timed": n_launch,
         "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
         "measured_int_peaks_Tops": {kk: v / 1e12 for kk, v in int_peak.items()},
         "frac_of_measured_lop3_peak": achieved / int_peak["lop3_ops_per_s"],
@@ -550,6 +553,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="C2")
+    ap.add_argument("--scan-variant", type=int, default=0,
+                    help="kernel A/B: 0 bit-sliced with k-mer pairing (default), 7 bit-sliced, 8 row-packed")
     ap.add_argument("--reads", type=int, default=0, help="override the reads per GPU of the workload (C5 sweep)")
     ap.add_argument("--lim", type=int, default=0, help="override the number of query k-mers (C5 sweep)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",

@@ -142,6 +142,8 @@ int apc_get_counts(apc_ctx *ctx, uint64_t *counts_out);
 uint64_t *apc_counts_device_ptr(apc_ctx *ctx);
 
 int apc_last_timing(const apc_ctx *ctx, apc_timing *out);
+/* Kernels launched by the most recent apc_scan (no synchronisation). */
+uint64_t apc_last_scan_launches(const apc_ctx *ctx);
 
 /* Tuning / test knobs.  "scan_variant": 0 or 7 = bit-sliced kernel (reads
  * packed into words, the default), 8 = best row-packed kernel for k, 1 = one

@@ -48,5 +48,7 @@ if __name__ == "__main__":
                      (1000000, 150, 20, 5000)]:
             for variant in (0, 8):
                 print(json.dumps(run(c, *args, variant=variant, reps=3)), flush=True)
+        if len(sys.argv) > 1 and sys.argv[1] == "pairs":
+            sys.exit(0)
         for tpj in (1, 2, 4, 8):
             print(json.dumps(run(c, 100000, 100, 16, 2000, 0, tpj)), flush=True)
