@@ -328,7 +328,7 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
     if (bs) {
         // k-mers in scan order (pairs with a common prefix first), then the index of each in the caller's order
         std::vector<uint32_t> order;
-        c->n_pairs = apc::bs_pair_queries(kmers, n_kmers, k, c->variant.pairing(), order);
+        apc::bs_group_queries(kmers, n_kmers, k, c->variant.pairing(), order, c->n_quads, c->n_pairs);
         uint64_t *hk = (uint64_t *)c->h_pinned;
         uint32_t *hp = (uint32_t *)(hk + n_kmers);
         for (uint32_t i = 0; i < n_kmers; i++) {

@@ -86,7 +86,8 @@ struct Ctx {
     ScanVariant variant{1, 1};
     uint32_t n_groups = 0;
     uint64_t *d_kmers = nullptr; // bit-sliced kernel: the query k-mers (pair members first), then u32 perm[n]
-    uint32_t n_pairs = 0;        // pairs of k-mers with a common prefix >= k/2 (bs_pair_kernel)
+    uint32_t n_quads = 0;        // groups of four k-mers with a common prefix >= 3k/4 (bs_group_kernel<.., 4>)
+    uint32_t n_pairs = 0;        // pairs of k-mers with a common prefix >= k/2 (bs_group_kernel<.., 2>)
     size_t kmers_cap = 0;
     uint32_t *d_peq = nullptr; // [n_groups][5][4]
     size_t peq_cap = 0;
@@ -144,7 +145,8 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
 cudaError_t launch_build_planes(const Ctx &c);
 cudaError_t launch_bs_scan(const Ctx &c, uint64_t read_lo, uint64_t read_hi, unsigned long long *d_counts,
                            uint32_t sg_per_job, uint64_t *launches);
-uint32_t bs_pair_queries(const uint64_t *kmers, uint32_t n, int k, bool enable, std::vector<uint32_t> &order);
+void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, bool enable, std::vector<uint32_t> &order,
+                      uint32_t &n_quads, uint32_t &n_pairs);
 int bs_warps_per_sm(int k);
 
 // exact_kernels.cu

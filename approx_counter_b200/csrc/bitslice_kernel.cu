@@ -48,6 +48,8 @@ constexpr int bs_warps_per_sm_c(int k) {
     // 24 -> 80 registers, 20 -> 96, 16 -> 128, 12 -> 168, 8 -> 255
     return k <= 8 ? 24 : k <= 12 ? 20 : k <= 16 ? 16 : k <= 24 ? 12 : 8;
 }
+// the quad kernel carries 3(3k/4 + 4(k - 3k/4)) state registers: built where that fits without spills
+constexpr bool bs_quads_ok(int k) { return k >= 8 && k <= 20; }
 constexpr int kPlaneRow = 128;      // bytes between the A, C, G, T rows of the per-warp mask slot
 
 // ---- K2b: scan tiles -> bit planes ------------------------------------------------------
@@ -210,18 +212,19 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
     }
 }
 
-// Two k-mers with a common prefix of at least P bases per warp.  Rows 0..P-1 of their tables
-// are identical in every column, so they are computed once: 5(2K - P) instead of 10K LOP3 per
-// column.  The query k-mers of the reference's pipeline are the most frequent k-mers of the
+// G k-mers with a common prefix of at least P bases per warp.  Rows 0..P-1 of their tables
+// are identical in every column, so they are computed once: 5(P + G(K-P)) instead of 5GK LOP3
+// per column.  The query k-mers of the reference's pipeline are the most frequent k-mers of the
 // sample, i.e. mostly an adapter's windows and their one-error variants, which share long
-// prefixes once sorted (C2: two thirds of the 2000 k-mers pair up at P = 8).
-template <int K, int P, int MB>
+// prefixes once sorted (C2: quads with P = 3k/4 and pairs with P = k/2 cut the row work to 0.71).
+// kmers[G*u .. G*u+G-1] are the k-mers of unit u, perm[] their indices in the caller's order.
+template <int K, int P, int G, int MB>
 __global__ void __launch_bounds__(32, MB)
-bs_pair_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const uint32_t n_sg, const uint32_t cols,
-               const uint32_t read_len, const uint64_t range_lo, const uint64_t range_hi,
-               const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ perm, const uint32_t n_units,
-               const uint32_t sg_per_job, const uint32_t n_jobs, unsigned long long *__restrict__ counts,
-               unsigned int *__restrict__ job_counter) {
+bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const uint32_t n_sg, const uint32_t cols,
+                const uint32_t read_len, const uint64_t range_lo, const uint64_t range_hi,
+                const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ perm, const uint32_t n_units,
+                const uint32_t sg_per_job, const uint32_t n_jobs, unsigned long long *__restrict__ counts,
+                unsigned int *__restrict__ job_counter) {
     constexpr int T = K - P; // rows of the private tails
     static_assert(P >= 2 && T >= 1, "the always-matching rows 0..1 must lie in the shared part");
     __shared__ __align__(16) uint32_t s_mask[2][4 * kGroupsPerSuper];
@@ -232,54 +235,68 @@ bs_pair_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
         const uint32_t job = bs_next_job(job_counter, n_jobs, lane);
         if (job >= n_jobs) break;
         const uint32_t u = job % n_units, jb = job / n_units;
-        const uint64_t ka = __ldg(kmers + 2 * u), kb = __ldg(kmers + 2 * u + 1);
-        uint32_t off_s[P], off_a[T], off_b[T];
+        uint32_t off_s[P], off_t[G][T];
+        {
+            const uint64_t k0 = __ldg(kmers + (size_t)G * u);
 #pragma unroll
-        for (int i = 0; i < P; i++) off_s[i] = (uint32_t)((ka >> (2 * (K - 1 - i))) & 3u) * kPlaneRow;
-#pragma unroll
-        for (int i = 0; i < T; i++) {
-            off_a[i] = (uint32_t)((ka >> (2 * (T - 1 - i))) & 3u) * kPlaneRow;
-            off_b[i] = (uint32_t)((kb >> (2 * (T - 1 - i))) & 3u) * kPlaneRow;
+            for (int i = 0; i < P; i++) off_s[i] = (uint32_t)((k0 >> (2 * (K - 1 - i))) & 3u) * kPlaneRow;
         }
-        uint32_t cnt_a = 0, cnt_b = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const uint64_t kg = __ldg(kmers + (size_t)G * u + g);
+#pragma unroll
+            for (int i = 0; i < T; i++) off_t[g][i] = (uint32_t)((kg >> (2 * (T - 1 - i))) & 3u) * kPlaneRow;
+        }
+        uint32_t cnt[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) cnt[g] = 0;
         const uint32_t sg_end = min(n_sg, (jb + 1) * sg_per_job);
         for (uint32_t sg = jb * sg_per_job; sg < sg_end; sg++) {
-            uint32_t s0[P], s1[P], s2[P], x0[T], x1[T], x2[T], y0[T], y1[T], y2[T];
+            uint32_t s0[P], s1[P], s2[P], x0[G][T], x1[G][T], x2[G][T], a0[G], a1[G], a2[G];
             bs_rows_init<P, 0>(s0, s1, s2);
-            bs_rows_init<T, P>(x0, x1, x2);
-            bs_rows_init<T, P>(y0, y1, y2);
-            uint32_t a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                bs_rows_init<T, P>(x0[g], x1[g], x2[g]);
+                a0[g] = a1[g] = a2[g] = 0;
+            }
             const uint4 *p = planes + ((size_t)(sg_first + sg) * cols) * kGroupsPerSuper + lane;
             uint4 ma = __ldg(p), mb = __ldg(p + kGroupsPerSuper);
             for (uint32_t pr = 0; pr < pairs; pr++) {
                 p += 2 * kGroupsPerSuper;
                 const uint4 na = __ldg(p), nb = __ldg(p + kGroupsPerSuper);
                 APC_BS_STAGE_MASKS()
-                uint32_t ha[3], hb[3];
+                uint32_t h0[G], h1[G], h2[G];
 #pragma unroll
                 for (int col = 0; col < 2; col++) {
                     const char *slot = reinterpret_cast<const char *>(s_mask[col]) + lane * 4;
                     BsCarry c = bs_carry_init();
                     bs_rows<P, 0>(s0, s1, s2, c, slot, off_s);
-                    BsCarry cb = c;
-                    bs_rows<T, P>(x0, x1, x2, c, slot, off_a);
-                    bs_rows<T, P>(y0, y1, y2, cb, slot, off_b);
-                    if (col == 0) {
-                        ha[0] = x0[T - 1]; ha[1] = x1[T - 1]; ha[2] = x2[T - 1];
-                        hb[0] = y0[T - 1]; hb[1] = y1[T - 1]; hb[2] = y2[T - 1];
+#pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        BsCarry cg = c;
+                        bs_rows<T, P>(x0[g], x1[g], x2[g], cg, slot, off_t[g]);
+                        if (col == 0) {
+                            h0[g] = x0[g][T - 1]; h1[g] = x1[g][T - 1]; h2[g] = x2[g][T - 1];
+                        }
                     }
                 }
-                a0 = or3(a0, ha[0], x0[T - 1]); a1 = or3(a1, ha[1], x1[T - 1]); a2 = or3(a2, ha[2], x2[T - 1]);
-                b0 = or3(b0, hb[0], y0[T - 1]); b1 = or3(b1, hb[1], y1[T - 1]); b2 = or3(b2, hb[2], y2[T - 1]);
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    a0[g] = or3(a0[g], h0[g], x0[g][T - 1]);
+                    a1[g] = or3(a1[g], h1[g], x1[g][T - 1]);
+                    a2[g] = or3(a2[g], h2[g], x2[g][T - 1]);
+                }
                 ma = na; mb = nb;
             }
             const uint32_t vm = bs_valid_mask(((uint64_t)(sg_first + sg) * kGroupsPerSuper + lane) * 32, range_lo, range_hi);
-            cnt_a += __popc(a0 & vm) + __popc(a1 & vm) + __popc(a2 & vm);
-            cnt_b += __popc(b0 & vm) + __popc(b1 & vm) + __popc(b2 & vm);
+#pragma unroll
+            for (int g = 0; g < G; g++) cnt[g] += __popc(a0[g] & vm) + __popc(a1[g] & vm) + __popc(a2[g] & vm);
         }
-        const uint32_t ta = __reduce_add_sync(0xFFFFFFFFu, cnt_a), tb = __reduce_add_sync(0xFFFFFFFFu, cnt_b);
-        if (lane == 0 && ta) atomicAdd(&counts[__ldg(perm + 2 * u)], (unsigned long long)ta);
-        if (lane == 0 && tb) atomicAdd(&counts[__ldg(perm + 2 * u + 1)], (unsigned long long)tb);
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, cnt[g]);
+            if (lane == 0 && t) atomicAdd(&counts[__ldg(perm + (size_t)G * u + g)], (unsigned long long)t);
+        }
     }
 }
 
@@ -288,37 +305,52 @@ struct BsRange {
     uint64_t lo, hi;
 };
 
+template <int K, int P, int G>
+static cudaError_t launch_bs_group(const Ctx &c, const BsRange &r, unsigned long long *d_counts, uint32_t sg_blocks,
+                                   uint32_t sg_per_job, uint32_t first_kmer, uint32_t n_units, uint64_t *launches) {
+    constexpr int MB = bs_warps_per_sm_c(P + G * (K - P)); // same register need as a single k-mer of that many rows
+    const uint64_t jobs = (uint64_t)sg_blocks * n_units;
+    if (jobs > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+    const uint32_t *perm = reinterpret_cast<const uint32_t *>(c.d_kmers + c.n_kmers);
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c.sm_count * MB, jobs);
+    bs_group_kernel<K, P, G, MB><<<grid, 32, 0, c.stream>>>(
+        c.d_planes, r.sg_first, r.n_sg, c.chunks * kChunkBases, c.max_len, r.lo, r.hi, c.d_kmers + first_kmer,
+        perm + first_kmer, n_units, sg_per_job, (uint32_t)jobs, d_counts, c.d_job_counter);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) (*launches)++;
+    return e;
+}
+
 template <int K>
 static cudaError_t launch_bs_k(const Ctx &c, const BsRange &r, unsigned long long *d_counts, uint32_t sg_per_job,
                                uint64_t *launches) {
     const uint32_t sg_blocks = (r.n_sg + sg_per_job - 1) / sg_per_job;
-    const uint32_t cols = c.chunks * kChunkBases;
-    const uint32_t *perm = reinterpret_cast<const uint32_t *>(c.d_kmers + c.n_kmers);
-    // pairs first (the longer jobs), then the k-mers that found no partner
-    if constexpr (K >= 4) if (c.n_pairs) {
-        constexpr int P = K / 2;
-        constexpr int MB = bs_warps_per_sm_c(2 * K - P);
-        const uint64_t jobs = (uint64_t)sg_blocks * c.n_pairs;
-        if (jobs > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
-        const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c.sm_count * MB, jobs);
-        bs_pair_kernel<K, P, MB><<<grid, 32, 0, c.stream>>>(c.d_planes, r.sg_first, r.n_sg, cols, c.max_len, r.lo, r.hi,
-                                                            c.d_kmers, perm, c.n_pairs, sg_per_job, (uint32_t)jobs,
-                                                            d_counts, c.d_job_counter);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        (*launches)++;
+    // quads first (the longest jobs), then pairs, then the k-mers that found no partner
+    if constexpr (bs_quads_ok(K)) {
+        if (c.n_quads) {
+            cudaError_t e = launch_bs_group<K, 3 * K / 4, 4>(c, r, d_counts, sg_blocks, sg_per_job, 0, c.n_quads, launches);
+            if (e != cudaSuccess) return e;
+        }
     }
-    const uint32_t n_single = c.n_kmers - 2 * c.n_pairs;
+    if constexpr (K >= 4) {
+        if (c.n_pairs) {
+            cudaError_t e = launch_bs_group<K, K / 2, 2>(c, r, d_counts, sg_blocks, sg_per_job, 4 * c.n_quads, c.n_pairs, launches);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    const uint32_t first_single = 4 * c.n_quads + 2 * c.n_pairs;
+    const uint32_t n_single = c.n_kmers - first_single;
     if (n_single) {
         // registers: 3K of state + the row masks of two columns in flight (ptxas wants about 6K + 26);
         // CTAs (= warps) per SM chosen so that nothing spills
         constexpr int MB = bs_warps_per_sm_c(K);
         const uint64_t jobs = (uint64_t)sg_blocks * n_single;
         if (jobs > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+        const uint32_t *perm = reinterpret_cast<const uint32_t *>(c.d_kmers + c.n_kmers);
         const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c.sm_count * MB, jobs);
-        bs_scan_kernel<K, MB><<<grid, 32, 0, c.stream>>>(c.d_planes, r.sg_first, r.n_sg, cols, c.max_len, r.lo, r.hi,
-                                                         c.d_kmers + 2 * c.n_pairs, perm + 2 * c.n_pairs, n_single,
-                                                         sg_per_job, (uint32_t)jobs, d_counts, c.d_job_counter);
+        bs_scan_kernel<K, MB><<<grid, 32, 0, c.stream>>>(c.d_planes, r.sg_first, r.n_sg, c.chunks * kChunkBases, c.max_len,
+                                                         r.lo, r.hi, c.d_kmers + first_single, perm + first_single,
+                                                         n_single, sg_per_job, (uint32_t)jobs, d_counts, c.d_job_counter);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         (*launches)++;
@@ -328,18 +360,39 @@ static cudaError_t launch_bs_k(const Ctx &c, const BsRange &r, unsigned long lon
 
 int bs_warps_per_sm(int k) { return bs_warps_per_sm_c(k); }
 
-// Host side of the pairing: sort the k-mers, pair neighbours whose common prefix is at least
-// k/2 bases.  order[] receives the k-mer indices, the 2*n_pairs pair members first.
-uint32_t bs_pair_queries(const uint64_t *kmers, uint32_t n, int k, bool enable, std::vector<uint32_t> &order) {
+// Host side of the grouping: sort the k-mers, then greedily take runs of four neighbours whose
+// common prefix is at least 3k/4 bases (where the quad kernel exists), then pairs of neighbours
+// with a common prefix of at least k/2.  order[] receives the k-mer indices: quad members
+// first, then pair members, then the rest.
+bool bs_quads_available(int k) { return bs_quads_ok(k); }
+
+void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, bool enable, std::vector<uint32_t> &order,
+                      uint32_t &n_quads, uint32_t &n_pairs) {
     order.resize(n);
     for (uint32_t i = 0; i < n; i++) order[i] = i;
-    if (!enable || k < 4 || n < 2) return 0;
+    n_quads = n_pairs = 0;
+    if (!enable || k < 4 || n < 2) return;
     std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return kmers[a] != kmers[b] ? kmers[a] < kmers[b] : a < b; });
-    const int p = k / 2;
-    std::vector<uint32_t> pairs, singles;
-    pairs.reserve(n);
+    auto share = [&](uint32_t i, uint32_t j, int p) { // sorted positions i < j: common prefix of at least p bases
+        return ((kmers[order[i]] ^ kmers[order[j]]) >> (2 * (k - p))) == 0;
+    };
+    std::vector<uint8_t> used(n, 0);
+    std::vector<uint32_t> quads, pairs, singles;
+    if (bs_quads_ok(k)) {
+        const int p4 = 3 * k / 4;
+        for (uint32_t i = 0; i + 3 < n;) {
+            if (share(i, i + 3, p4)) { // sorted, so the two in between share it too
+                for (int t = 0; t < 4; t++) { quads.push_back(order[i + t]); used[i + t] = 1; }
+                i += 4;
+            } else {
+                i += 1;
+            }
+        }
+    }
+    const int p2 = k / 2;
     for (uint32_t i = 0; i < n;) {
-        if (i + 1 < n && ((kmers[order[i]] ^ kmers[order[i + 1]]) >> (2 * (k - p))) == 0) {
+        if (used[i]) { i++; continue; }
+        if (i + 1 < n && !used[i + 1] && share(i, i + 1, p2)) {
             pairs.push_back(order[i]);
             pairs.push_back(order[i + 1]);
             i += 2;
@@ -348,10 +401,11 @@ uint32_t bs_pair_queries(const uint64_t *kmers, uint32_t n, int k, bool enable, 
             i += 1;
         }
     }
-    const uint32_t n_pairs = (uint32_t)(pairs.size() / 2);
-    std::copy(pairs.begin(), pairs.end(), order.begin());
-    std::copy(singles.begin(), singles.end(), order.begin() + pairs.size());
-    return n_pairs;
+    n_quads = (uint32_t)(quads.size() / 4);
+    n_pairs = (uint32_t)(pairs.size() / 2);
+    std::copy(quads.begin(), quads.end(), order.begin());
+    std::copy(pairs.begin(), pairs.end(), order.begin() + quads.size());
+    std::copy(singles.begin(), singles.end(), order.begin() + quads.size() + pairs.size());
 }
 
 cudaError_t launch_bs_scan(const Ctx &c, uint64_t lo, uint64_t hi, unsigned long long *d_counts, uint32_t sg_per_job,

@@ -451,14 +451,15 @@ def run_b200(args, w):
     sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     alu_peak = sms * 4 * 16 * sm_max * 1e6  # ALU pipe: 16 lanes/clk/SMSP (B300_MICROARCH.md:85)
-    # a scan is one or two launches (k-mer pairs, then the unpaired k-mers): the roofline unit is the scan
+    # a scan is up to three launches (k-mer quads, pairs, then the ungrouped k-mers): the roofline unit is the scan
     n_scans = max(len(kernel_events), 1)
     per_launch_s = kern_ms / 1e3 / n_scans
     cols_launch = cols_rank / 2.0
-    # no kernel can retire more than one instruction per SMSP per clock; a faster reading means
-    # the event pairs did not contain the kernel (e.g. it ran on another stream)
+    # no kernel can retire more than one instruction per SMSP per clock, and even four k-mers sharing 3k/4 of
+    # their rows cost 5 * 7k/16 / 32 > 0.5 lane-operations per column; a faster reading means the event pairs
+    # did not contain the kernel (e.g. it ran on another stream)
     issue_peak = sms * 4 * 32 * sm_max * 1e6
-    if 4.0 * cols_launch / per_launch_s > issue_peak:
+    if 0.5 * cols_launch / per_launch_s > issue_peak:
         raise SystemExit("bench.py: implausible kernel time — the timed region did not contain the scan kernel")
     achieved = ALGO_OPS_PER_COLUMN * cols_launch / per_launch_s
     traffic = ncu_alu = None
@@ -473,7 +474,7 @@ def run_b200(args, w):
     cols_padded = ((sl + 1 + 15) // 16) * 16
     hbm_bytes_launch = ((n + 1023) // 1024) * 32 * cols_padded * 16 + 16 * q_start
     roofline = {
-        "bound": "int-alu", "kernel": "bs_pair_kernel + bs_scan_kernel (one scan)", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
+        "bound": "int-alu", "kernel": "bs_group_kernel<G=4>, bs_group_kernel<G=2>, bs_scan_kernel (one scan = up to three launches)", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
         "unit": "Tint-op/s", "frac": achieved / alu_peak, "traffic": traffic, "ncu_alu_pipe_pct": ncu_alu,
         "peak_source": f"ALU pipe nominal = {sms} SM x 4 SMSP x 16 lanes/clk x {sm_max:.0f} MHz (SURVEY.md §8d)",
         "algorithmic_ops_per_column": ALGO_OPS_PER_COLUMN, "columns_per_launch": cols_launch,

@@ -242,4 +242,4 @@ def test_prefix_sharing_kmers_are_paired_correctly(counter, k):
             counter.set_option("scan_variant", 0)
         assert np.array_equal(got, want), variant
         if variant == 0:
-            assert t["scan_launches"] == 2      # pairs kernel + singles kernel
+            assert t["scan_launches"] in (2, 3)  # (quads kernel,) pairs kernel, singles kernel
