@@ -194,3 +194,21 @@ class ApproxCounter:
 def device_count():
     n = _lib.load().apc_device_count()
     return max(0, n)
+
+
+def plan_queries(kmers, k):
+    """The scan plan of the default kernel for these k-mers (apc_plan_queries; needs no GPU):
+    dict(order, reversed, units, shape_t, shape_g) — see include/apc.h."""
+    lib = _lib.load()
+    km = _as_kmers(kmers)
+    n = len(km)
+    order = np.zeros(n, np.uint32)
+    rev = np.zeros(n, np.uint8)
+    units = np.zeros(8, np.uint32)
+    st = np.zeros(8, np.int32)
+    sg = np.zeros(8, np.int32)
+    rc = lib.apc_plan_queries(int(k), km.ctypes.data, n, order.ctypes.data, rev.ctypes.data, units.ctypes.data,
+                              st.ctypes.data, sg.ctypes.data)
+    if rc != 0:
+        raise ApcError(rc, "apc_plan_queries")
+    return {"order": order, "reversed": rev, "units": units, "shape_t": st, "shape_g": sg}

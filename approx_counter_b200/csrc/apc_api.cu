@@ -67,11 +67,11 @@ static int prepare_sample(Ctx *c, uint64_t n_reads, uint32_t max_len, uint64_t t
     const size_t tiles_bytes = ((size_t)c->n_tiles * c->chunks + 1) * kTileReads * sizeof(uint4);
     int st = grow(c, c->d_tiles, c->tiles_bytes, tiles_bytes);
     if (st) return st;
-    // bit planes: 32 tiles per super-group, one uint4 per (column, tile), + two columns of padding
-    // for the kernel's prefetch
+    // bit planes: 32 tiles per super-group, one uint4 per (column, tile), + two columns of padding at
+    // either end for the kernels' prefetch (forward and backward walks)
     const size_t n_sg = ((size_t)c->n_tiles + 31) / 32;
     c->planes_bytes = n_sg * c->chunks * kChunkBases * 32 * sizeof(uint4);
-    if ((st = grow(c, c->d_planes, c->planes_cap, c->planes_bytes + 2 * 32 * sizeof(uint4)))) return st;
+    if ((st = grow(c, c->d_planes, c->planes_cap, c->planes_bytes + 4 * 32 * sizeof(uint4)))) return st;
     const size_t lens_bytes = ((size_t)c->n_tiles * kTileReads + 1) * sizeof(uint32_t);
     if ((st = grow(c, c->d_lens, c->lens_cap, lens_bytes))) return st;
     APC_CUDA(c, cudaMemsetAsync(c->d_lens, 0, lens_bytes, c->stream));
@@ -124,8 +124,13 @@ int apc_create(int device, apc_ctx **out) {
     for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_table, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_job_counter, sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(c->d_job_counter, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_job_counter, (apc::kBsShapes + 1) * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_job_counter, 0, (apc::kBsShapes + 1) * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->bs_fork, cudaEventDisableTiming);
+    for (int i = 0; i < apc::kBsShapes && e == cudaSuccess; i++) {
+        e = cudaStreamCreateWithFlags(&c->bs_streams[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->bs_join[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         apc_destroy(c);
         return APC_ERR_CUDA;
@@ -153,6 +158,11 @@ void apc_destroy(apc_ctx *c) {
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
     if (c->ev_table) cudaEventDestroy(c->ev_table);
+    if (c->bs_fork) cudaEventDestroy(c->bs_fork);
+    for (int i = 0; i < apc::kBsShapes; i++) {
+        if (c->bs_join[i]) cudaEventDestroy(c->bs_join[i]);
+        if (c->bs_streams[i]) cudaStreamDestroy(c->bs_streams[i]);
+    }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -299,6 +309,7 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
     if (st) return st;
     if (k < 2 || k > 32) return apc::fail(c, APC_ERR_INVALID, "k must be in [2,32]");
     if (!kmers && n_kmers) return apc::fail(c, APC_ERR_INVALID, "kmers is NULL");
+    if (n_kmers > 0x7FFFFFFFu) return apc::fail(c, APC_ERR_INVALID, "too many k-mers");
     if (k < 32)
         for (uint32_t i = 0; i < n_kmers; i++)
             if (kmers[i] >> (2 * k)) return apc::fail(c, APC_ERR_INVALID, "k-mer value wider than 2k bits");
@@ -326,14 +337,16 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
     }
     void *d_dst = nullptr;
     if (bs) {
-        // k-mers in scan order (pairs with a common prefix first), then the index of each in the caller's order
+        // k-mers in scan order (units of prefix- or suffix-sharing k-mers first, shape by shape), then the
+        // index of each in the caller's order; bit 31 marks the members of a unit that is scanned backwards
         std::vector<uint32_t> order;
-        apc::bs_group_queries(kmers, n_kmers, k, c->variant.pairing(), order, c->n_quads, c->n_pairs);
+        std::vector<uint8_t> reversed;
+        apc::bs_group_queries(kmers, n_kmers, k, c->variant.pairing() ? c->opt_shape_mask : 0u, order, reversed, c->bs_units);
         uint64_t *hk = (uint64_t *)c->h_pinned;
         uint32_t *hp = (uint32_t *)(hk + n_kmers);
         for (uint32_t i = 0; i < n_kmers; i++) {
-            hk[i] = kmers[order[i]];
-            hp[i] = order[i];
+            hk[i] = reversed[i] ? apc::bs_reverse_kmer(kmers[order[i]], k) : kmers[order[i]];
+            hp[i] = order[i] | (reversed[i] ? 0x80000000u : 0u);
         }
         c->n_groups = n_kmers;
         if ((st = apc::grow(c, c->d_kmers, c->kmers_cap, table_words * sizeof(uint32_t)))) return st;
@@ -350,6 +363,31 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
                                     c->stream));
         APC_CUDA(c, cudaEventRecord(c->ev_table, c->stream));
         c->table_copy_pending = true;
+    }
+    return APC_OK;
+}
+
+int apc_plan_queries(uint8_t k, const uint64_t *kmers, uint32_t n_kmers, uint32_t *order_out, uint8_t *reversed_out,
+                     uint32_t *units_out, int32_t *shape_t_out, int32_t *shape_g_out) {
+    static_assert(APC_PLAN_SHAPES == apc::kBsShapes, "apc.h and apc_internal.h disagree on the number of shapes");
+    if (k < 2 || k > 32 || (!kmers && n_kmers) || n_kmers > 0x7FFFFFFFu) return APC_ERR_INVALID;
+    try {
+        std::vector<uint32_t> order;
+        std::vector<uint8_t> reversed;
+        uint32_t units[apc::kBsShapes];
+        apc::bs_group_queries(kmers, n_kmers, k, 0xFFFFFFFFu, order, reversed, units);
+        for (uint32_t i = 0; i < n_kmers; i++) {
+            if (order_out) order_out[i] = order[i];
+            if (reversed_out) reversed_out[i] = reversed[i];
+        }
+        for (int s = 0; s < apc::kBsShapes; s++) {
+            const apc::BsShape sh = apc::bs_shape(k, s);
+            if (units_out) units_out[s] = units[s];
+            if (shape_t_out) shape_t_out[s] = sh.g ? sh.t : 0;
+            if (shape_g_out) shape_g_out[s] = sh.g;
+        }
+    } catch (...) {
+        return APC_ERR_NOMEM;
     }
     return APC_OK;
 }
@@ -428,6 +466,11 @@ int apc_set_option(apc_ctx *c, const char *name, int64_t value) {
     if (!std::strcmp(name, "tiles_per_job")) {
         if (value < 0 || value > (1 << 20)) return apc::fail(c, APC_ERR_INVALID, "tiles_per_job out of range");
         c->opt_tiles_per_job = (int)value;
+        return APC_OK;
+    }
+    if (!std::strcmp(name, "shape_mask")) { // takes effect at the next apc_set_queries
+        if (value < 0 || value > 0xFFFFFFFFll) return apc::fail(c, APC_ERR_INVALID, "shape_mask out of range");
+        c->opt_shape_mask = (uint32_t)value;
         return APC_OK;
     }
     if (!std::strcmp(name, "scan_first_read")) {

@@ -28,6 +28,30 @@ constexpr int kPeqRows = 5;        // A C G T N
 constexpr int kWordsPerThread = 4; // u32 state words per thread = one 16-byte table row
 constexpr int kScanWarps = 8;      // warps per CTA of the scan kernel
 
+// ---- bit-sliced kernel: unit shapes -----------------------------------------------------------
+// A unit is G k-mers that share their first K - T bases (rows) and is scanned by one warp
+// (bs_group_kernel<K, K - T, G>).  bs_shape(k, s) is shape s of the table for this k, g == 0 where
+// the shape does not exist (fewer than two shared rows, or more rows than the register file holds
+// without spills).  Heaviest units first: that is also the launch order.
+struct BsShape {
+    int t, g;
+};
+constexpr int kBsShapes = 8;
+constexpr int kBsMaxRows = 48;
+constexpr BsShape bs_shape(int k, int s) {
+    const BsShape table[kBsShapes] = {{5, 6}, {8, 4}, {6, 3}, {2, 8}, {3, 6}, {3, 4}, {1, 4}, {k - k / 2, 2}};
+    const BsShape sh = table[s];
+    const int p = k - sh.t;
+    if (p < 2 || sh.t < 1 || p + sh.g * sh.t > kBsMaxRows) return BsShape{0, 0};
+    for (int j = 0; j < s; j++)
+        if (table[j].t == sh.t && table[j].g == sh.g) return BsShape{0, 0};
+    return sh;
+}
+struct BsRange { // super-groups (1024 reads) and reads [lo, hi) of one scan
+    uint32_t sg_first, n_sg;
+    uint64_t lo, hi;
+};
+
 struct ScanVariant {
     int nw; // u32 words per unit (1 or 2); 0 = bit-sliced kernel (bitslice_kernel.cu)
     int f;  // k-mers interleaved per unit
@@ -68,8 +92,10 @@ struct Ctx {
     // sample
     uint4 *d_tiles = nullptr;
     size_t tiles_bytes = 0;
-    uint4 *d_planes = nullptr;  // bit planes of the same text (bitslice_kernel.cu), [super-group][column][32 groups]
+    uint4 *d_planes = nullptr;  // bit planes of the same text (bitslice_kernel.cu), [super-group][column][32 groups],
+                                // two columns of padding in front and behind (the kernels prefetch past both ends)
     size_t planes_cap = 0, planes_bytes = 0;
+    uint4 *planes() const { return d_planes + 2 * 32; }
     uint32_t *d_lens = nullptr; // per-read length — exact stage
     size_t lens_cap = 0;
     bool has_sample = false;
@@ -85,15 +111,19 @@ struct Ctx {
     uint32_t n_kmers = 0;
     ScanVariant variant{1, 1};
     uint32_t n_groups = 0;
-    uint64_t *d_kmers = nullptr; // bit-sliced kernel: the query k-mers (pair members first), then u32 perm[n]
-    uint32_t n_quads = 0;        // groups of four k-mers with a common prefix >= 3k/4 (bs_group_kernel<.., 4>)
-    uint32_t n_pairs = 0;        // pairs of k-mers with a common prefix >= k/2 (bs_group_kernel<.., 2>)
+    uint64_t *d_kmers = nullptr; // bit-sliced kernel: the query k-mers in scan order (units of shape 0, 1, ..., then
+                                 // the ungrouped ones; members of suffix-sharing units reversed), then u32 perm[n]
+    uint32_t bs_units[kBsShapes] = {}; // units per shape
     size_t kmers_cap = 0;
     uint32_t *d_peq = nullptr; // [n_groups][5][4]
     size_t peq_cap = 0;
     unsigned long long *d_counts = nullptr; // [n_groups * queries_per_group]
     size_t counts_cap = 0;
-    unsigned int *d_job_counter = nullptr;  // job queue head of the persistent scan kernel (self re-arming)
+    unsigned int *d_job_counter = nullptr;  // job queue heads of the persistent scan kernels (self re-arming), one per
+                                            // concurrent launch: [kBsShapes + 1]
+    cudaStream_t bs_streams[kBsShapes] = {}; // side streams of the bit-sliced scan (one launch per shape, concurrent)
+    cudaEvent_t bs_join[kBsShapes] = {};
+    cudaEvent_t bs_fork = nullptr;
 
     // staging
     uint8_t *d_stage = nullptr;
@@ -106,6 +136,7 @@ struct Ctx {
     // options
     int opt_variant = 0;
     int opt_tiles_per_job = 0;
+    uint32_t opt_shape_mask = 0xFFFFFFFFu; // unit shapes the bit-sliced scan may use (bit s = shape s of bs_shape)
     uint64_t opt_first_read = 0;  // scan only reads [first, first+n) of the resident sample
     int64_t opt_n_reads = -1;     // -1 = to the end
 
@@ -145,9 +176,9 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
 cudaError_t launch_build_planes(const Ctx &c);
 cudaError_t launch_bs_scan(const Ctx &c, uint64_t read_lo, uint64_t read_hi, unsigned long long *d_counts,
                            uint32_t sg_per_job, uint64_t *launches);
-void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, bool enable, std::vector<uint32_t> &order,
-                      uint32_t &n_quads, uint32_t &n_pairs);
-int bs_warps_per_sm(int k);
+void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_mask, std::vector<uint32_t> &order,
+                      std::vector<uint8_t> &reversed, uint32_t (&units)[kBsShapes]);
+uint64_t bs_reverse_kmer(uint64_t kmer, int k);
 
 // exact_kernels.cu
 int exact_count_select(Ctx *c, uint8_t k, float lc_adjusted, uint64_t lim, uint64_t solid_km,

@@ -1,0 +1,327 @@
+// bitslice_core.cuh — the bit-sliced scan kernels (K1) and their per-k launcher.  Included by
+// bitslice_part.cu, which is compiled once per slice of k so that the ~250 instantiations
+// build in parallel.  See bitslice_kernel.cu for the design notes.
+#pragma once
+
+#include <algorithm>
+
+#include "apc_internal.h"
+#include "scan_core.cuh"
+
+namespace apc {
+
+constexpr int kGroupsPerSuper = 32; // lanes
+constexpr int kPlaneRow = 128;      // bytes between the A, C, G, T rows of the per-warp mask slot
+
+constexpr int bs_warps_per_sm_c(int rows) {
+#ifdef APC_BS_MB_OVERRIDE
+    (void)rows;
+    return APC_BS_MB_OVERRIDE; // A/B builds (tools/build_ab.sh)
+#endif
+    // registers are handed out per SM sub-partition (16384 each), so only multiples of 4 warps matter:
+    // 24 -> 80 registers, 20 -> 96, 16 -> 128, 12 -> 168, 8 -> 255
+    return rows <= 8 ? 24 : rows <= 12 ? 20 : rows <= 16 ? 16 : rows <= 24 ? 12 : 8;
+}
+
+// Values handed from row i-1 to row i inside one column.
+struct BsCarry {
+    uint32_t p0, p1, p2; // previous column's row i-1, levels 0..2 (row -1 = empty prefix: always matches)
+    uint32_t n0p, n1p;   // this column's row i-1, levels 0 and 1
+};
+
+__device__ __forceinline__ BsCarry bs_carry_init() {
+    const uint32_t ALL = 0xFFFFFFFFu;
+    return BsCarry{ALL, ALL, ALL, ALL, ALL};
+}
+
+// N consecutive rows of one text column, the first of them being row FIRST of the k-mer: e_i
+// from the warp's mask slot (LDS with a uniform-register offset), then the five LOP3 of the row.
+template <int N, int FIRST>
+__device__ __forceinline__ void bs_rows(uint32_t (&r0)[N], uint32_t (&r1)[N], uint32_t (&r2)[N], BsCarry &c,
+                                        const char *slot_lane, const uint32_t (&off)[N]) {
+    const uint32_t ALL = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const int i = FIRST + j;
+        const uint32_t e = *reinterpret_cast<const uint32_t *>(slot_lane + off[j]);
+        const uint32_t o0 = r0[j], o1 = r1[j], o2 = r2[j];
+        const uint32_t n0 = i < 1 ? e : and2(c.p0, e);
+        // rows 0 (level 1) and 0..1 (level 2) always match: that many k-mer bases can be skipped
+        const uint32_t n1 = i < 1 ? ALL : or3(and_or(c.p1, e, o0), c.p0, c.n0p);
+        const uint32_t n2 = i < 2 ? ALL : or3(and_or(c.p2, e, o1), c.p1, c.n1p);
+        r0[j] = n0; r1[j] = n1; r2[j] = n2;
+        c.p0 = o0; c.p1 = o1; c.p2 = o2;
+        c.n0p = n0; c.n1p = n1;
+    }
+}
+
+template <int N, int FIRST>
+__device__ __forceinline__ void bs_rows_init(uint32_t (&r0)[N], uint32_t (&r1)[N], uint32_t (&r2)[N]) {
+    const uint32_t ALL = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        r0[j] = 0;
+        r1[j] = FIRST + j < 1 ? ALL : 0; // prefix 1 by one deletion
+        r2[j] = FIRST + j < 2 ? ALL : 0; // prefixes 1..2 by deletions
+    }
+}
+
+// mask of the reads of group (sg, lane) that lie inside the scanned range
+__device__ __forceinline__ uint32_t bs_valid_mask(uint64_t first, uint64_t range_lo, uint64_t range_hi) {
+    const uint32_t ALL = 0xFFFFFFFFu;
+    uint32_t vm = 0;
+    if (first < range_hi && first + 32 > range_lo) {
+        vm = ALL;
+        if (range_lo > first) vm &= ALL << (uint32_t)(range_lo - first);
+        if (range_hi < first + 32) vm &= ALL >> (uint32_t)(first + 32 - range_hi);
+    }
+    return vm;
+}
+
+// job fetch of the persistent warps: warp-uniform result (ptxas keeps it in uniform registers)
+__device__ __forceinline__ uint32_t bs_next_job(unsigned int *job_counter, uint32_t n_jobs, uint32_t lane) {
+    uint32_t job = 0;
+    if (lane == 0) {
+        job = atomicAdd(job_counter, 1u);
+        if (job == n_jobs + gridDim.x - 1u) atomicExch(job_counter, 0u); // last fetch of the launch re-arms the queue
+    }
+    return __shfl_sync(0xFFFFFFFFu, job, 0);
+}
+
+#define APC_BS_STAGE_MASKS()                                                                                          \
+    s_mask[0][lane] = ma.x; s_mask[0][32 + lane] = ma.y; s_mask[0][64 + lane] = ma.z; s_mask[0][96 + lane] = ma.w;   \
+    s_mask[1][lane] = mb.x; s_mask[1][32 + lane] = mb.y; s_mask[1][64 + lane] = mb.z; s_mask[1][96 + lane] = mb.w;
+
+// One k-mer per warp.  kmers[u] is the k-mer of unit u, perm[u] its index in the caller's order.
+template <int K, int MB>
+__global__ void __launch_bounds__(32, MB)
+bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const uint32_t n_sg, const uint32_t cols,
+               const uint32_t read_len, const uint64_t range_lo, const uint64_t range_hi,
+               const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ perm, const uint32_t n_units,
+               const uint32_t sg_per_job, const uint32_t n_jobs, unsigned long long *__restrict__ counts,
+               unsigned int *__restrict__ job_counter) {
+    __shared__ __align__(16) uint32_t s_mask[2][4 * kGroupsPerSuper];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t ALL = 0xFFFFFFFFu;
+    const uint32_t pairs = (read_len + 1) / 2; // an odd length is rounded up with one padding column (N: matches nothing)
+
+    for (;;) {
+        const uint32_t job = bs_next_job(job_counter, n_jobs, lane);
+        if (job >= n_jobs) break;
+        const uint32_t u = job % n_units, jb = job / n_units;
+        const uint64_t kmer = __ldg(kmers + u);
+        uint32_t off[K]; // byte offset of the mask row (A, C, G, T) that k-mer base i selects
+#pragma unroll
+        for (int i = 0; i < K; i++) off[i] = (uint32_t)((kmer >> (2 * (K - 1 - i))) & 3u) * kPlaneRow;
+
+        uint32_t cnt = 0;
+        const uint32_t sg_end = min(n_sg, (jb + 1) * sg_per_job);
+        for (uint32_t sg = jb * sg_per_job; sg < sg_end; sg++) {
+            uint32_t r0[K], r1[K], r2[K];
+            bs_rows_init<K, 0>(r0, r1, r2);
+            uint32_t a0 = 0, a1 = K <= 1 ? ALL : 0, a2 = K <= 2 ? ALL : 0;
+            const uint4 *p = planes + ((size_t)(sg_first + sg) * cols) * kGroupsPerSuper + lane;
+            uint4 ma = __ldg(p), mb = __ldg(p + kGroupsPerSuper);
+            for (uint32_t pr = 0; pr < pairs; pr++) {
+                p += 2 * kGroupsPerSuper;
+                const uint4 na = __ldg(p), nb = __ldg(p + kGroupsPerSuper); // buffer is padded by two columns
+                APC_BS_STAGE_MASKS()
+                BsCarry c = bs_carry_init();
+                bs_rows<K, 0>(r0, r1, r2, c, reinterpret_cast<const char *>(s_mask[0]) + lane * 4, off);
+                const uint32_t h0 = r0[K - 1], h1 = r1[K - 1], h2 = r2[K - 1];
+                c = bs_carry_init();
+                bs_rows<K, 0>(r0, r1, r2, c, reinterpret_cast<const char *>(s_mask[1]) + lane * 4, off);
+                a0 = or3(a0, h0, r0[K - 1]);
+                a1 = or3(a1, h1, r1[K - 1]);
+                a2 = or3(a2, h2, r2[K - 1]);
+                ma = na; mb = nb;
+            }
+            // hits of these 32 reads: [d<=0] + [d<=1] + [d<=2] (:589-593), reads outside the
+            // scanned range (padding of the last group, or a sub-range scan) masked out
+            const uint32_t vm = bs_valid_mask(((uint64_t)(sg_first + sg) * kGroupsPerSuper + lane) * 32, range_lo, range_hi);
+            cnt += __popc(a0 & vm) + __popc(a1 & vm) + __popc(a2 & vm);
+        }
+        const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, cnt);
+        if (lane == 0 && total) atomicAdd(&counts[__ldg(perm + u)], (unsigned long long)total);
+    }
+}
+
+// G k-mers with a common prefix of P = K - T bases per warp.  Rows 0..P-1 of their tables are
+// identical in every column, so they are computed once: 5(P + G T) instead of 5 G K LOP3 per
+// column.  The query k-mers of the reference's pipeline are the most frequent k-mers of the
+// sample, i.e. mostly an adapter's windows and their one-error variants, which share long
+// prefixes — or long SUFFIXES.  The minimum edit distance of a k-mer to the substrings of a read
+// is that of the reversed k-mer to the substrings of the reversed read, so a unit whose members
+// share a suffix is stored reversed (bit 31 of its first perm entry) and walks the columns from
+// the last to the first: same code, negative column stride.
+// kmers[G*u .. G*u+G-1] are the k-mers of unit u, perm[] their indices in the caller's order.
+template <int K, int P, int G, int MB>
+__global__ void __launch_bounds__(32, MB)
+bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const uint32_t n_sg, const uint32_t cols,
+                const uint32_t read_len, const uint64_t range_lo, const uint64_t range_hi,
+                const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ perm, const uint32_t n_units,
+                const uint32_t sg_per_job, const uint32_t n_jobs, unsigned long long *__restrict__ counts,
+                unsigned int *__restrict__ job_counter) {
+    constexpr int T = K - P; // rows of the private tails
+    static_assert(P >= 2 && T >= 1, "the always-matching rows 0..1 must lie in the shared part");
+    __shared__ __align__(16) uint32_t s_mask[2][4 * kGroupsPerSuper];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t pairs = (read_len + 1) / 2;
+
+    for (;;) {
+        const uint32_t job = bs_next_job(job_counter, n_jobs, lane);
+        if (job >= n_jobs) break;
+        const uint32_t u = job % n_units, jb = job / n_units;
+        uint32_t off_s[P], off_t[G][T];
+        {
+            const uint64_t k0 = __ldg(kmers + (size_t)G * u);
+#pragma unroll
+            for (int i = 0; i < P; i++) off_s[i] = (uint32_t)((k0 >> (2 * (K - 1 - i))) & 3u) * kPlaneRow;
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const uint64_t kg = __ldg(kmers + (size_t)G * u + g);
+#pragma unroll
+            for (int i = 0; i < T; i++) off_t[g][i] = (uint32_t)((kg >> (2 * (T - 1 - i))) & 3u) * kPlaneRow;
+        }
+        // direction of the walk: first column and the (signed) distance between consecutive columns
+        const bool reverse = (__ldg(perm + (size_t)G * u) >> 31) != 0;
+        const int64_t cstep = reverse ? -(int64_t)kGroupsPerSuper : (int64_t)kGroupsPerSuper;
+        const size_t col0 = reverse ? 2 * (size_t)pairs - 1 : 0;
+        uint32_t cnt[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) cnt[g] = 0;
+        const uint32_t sg_end = min(n_sg, (jb + 1) * sg_per_job);
+        for (uint32_t sg = jb * sg_per_job; sg < sg_end; sg++) {
+            uint32_t s0[P], s1[P], s2[P], x0[G][T], x1[G][T], x2[G][T], a0[G], a1[G], a2[G];
+            bs_rows_init<P, 0>(s0, s1, s2);
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                bs_rows_init<T, P>(x0[g], x1[g], x2[g]);
+                a0[g] = a1[g] = a2[g] = 0;
+            }
+            const uint4 *p = planes + ((size_t)(sg_first + sg) * cols + col0) * kGroupsPerSuper + lane;
+            uint4 ma = __ldg(p), mb = __ldg(p + cstep);
+            for (uint32_t pr = 0; pr < pairs; pr++) {
+                p += 2 * cstep;
+                const uint4 na = __ldg(p), nb = __ldg(p + cstep); // the buffer is padded by two columns at both ends
+                APC_BS_STAGE_MASKS()
+                uint32_t h0[G], h1[G], h2[G];
+#pragma unroll
+                for (int col = 0; col < 2; col++) {
+                    const char *slot = reinterpret_cast<const char *>(s_mask[col]) + lane * 4;
+                    BsCarry c = bs_carry_init();
+                    bs_rows<P, 0>(s0, s1, s2, c, slot, off_s);
+#pragma unroll
+                    for (int g = 0; g < G; g++) {
+                        BsCarry cg = c;
+                        bs_rows<T, P>(x0[g], x1[g], x2[g], cg, slot, off_t[g]);
+                        if (col == 0) {
+                            h0[g] = x0[g][T - 1]; h1[g] = x1[g][T - 1]; h2[g] = x2[g][T - 1];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    a0[g] = or3(a0[g], h0[g], x0[g][T - 1]);
+                    a1[g] = or3(a1[g], h1[g], x1[g][T - 1]);
+                    a2[g] = or3(a2[g], h2[g], x2[g][T - 1]);
+                }
+                ma = na; mb = nb;
+            }
+            const uint32_t vm = bs_valid_mask(((uint64_t)(sg_first + sg) * kGroupsPerSuper + lane) * 32, range_lo, range_hi);
+#pragma unroll
+            for (int g = 0; g < G; g++) cnt[g] += __popc(a0[g] & vm) + __popc(a1[g] & vm) + __popc(a2[g] & vm);
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const uint32_t t = __reduce_add_sync(0xFFFFFFFFu, cnt[g]);
+            if (lane == 0 && t)
+                atomicAdd(&counts[__ldg(perm + (size_t)G * u + g) & 0x7FFFFFFFu], (unsigned long long)t);
+        }
+    }
+}
+
+// ---- launch --------------------------------------------------------------------------------------
+// One launch per shape that has units, each on its own stream with its own job queue, so that the
+// persistent warps of the next shape fill the SMs as those of the previous one run out of jobs.
+struct BsLaunchCtx {
+    const Ctx *c;
+    BsRange r;
+    unsigned long long *d_counts;
+    uint32_t sg_per_job_opt; // 0 = choose per launch
+    uint64_t *launches;
+    int slot; // next stream / job counter
+};
+
+inline uint32_t bs_sg_per_job(const BsLaunchCtx &l, uint32_t n_units, int mb) {
+    if (l.sg_per_job_opt) return l.sg_per_job_opt;
+    // >= 32 jobs per resident warp where the work allows it (tail <= 3 %), jobs of at most 16 super-groups
+    const uint64_t warps = (uint64_t)l.c->sm_count * mb;
+    const uint64_t jobs1 = (uint64_t)l.r.n_sg * n_units;
+    return (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, jobs1 / (warps * 32)));
+}
+
+template <typename Kernel>
+static cudaError_t bs_launch_one(BsLaunchCtx &l, Kernel kernel, int mb, uint32_t first_kmer, uint32_t n_units) {
+    const Ctx &c = *l.c;
+    const uint32_t spj = bs_sg_per_job(l, n_units, mb);
+    const uint64_t jobs = (uint64_t)((l.r.n_sg + spj - 1) / spj) * n_units;
+    if (jobs > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
+    const uint32_t *perm = reinterpret_cast<const uint32_t *>(c.d_kmers + c.n_kmers);
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c.sm_count * mb, jobs);
+    const int slot = l.slot++;
+    cudaStream_t s = c.stream;
+    cudaError_t e;
+    if (slot > 0) { // fork: the side stream starts after everything queued on the caller's stream so far
+        s = c.bs_streams[slot - 1];
+        if ((e = cudaStreamWaitEvent(s, c.bs_fork, 0)) != cudaSuccess) return e;
+    }
+    kernel<<<grid, 32, 0, s>>>(c.planes(), l.r.sg_first, l.r.n_sg, c.chunks * kChunkBases, c.max_len, l.r.lo, l.r.hi,
+                              c.d_kmers + first_kmer, perm + first_kmer, n_units, spj, (uint32_t)jobs, l.d_counts,
+                              c.d_job_counter + slot);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    (*l.launches)++;
+    if (slot > 0) { // join
+        if ((e = cudaEventRecord(c.bs_join[slot - 1], s)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(c.stream, c.bs_join[slot - 1], 0)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+template <int K, int S>
+static cudaError_t bs_launch_shapes(BsLaunchCtx &l, uint32_t &first_kmer) {
+    if constexpr (S < kBsShapes) {
+        constexpr BsShape sh = bs_shape(K, S);
+        if constexpr (sh.g > 0) {
+            const uint32_t n_units = l.c->bs_units[S];
+            if (n_units) {
+                constexpr int MB = bs_warps_per_sm_c(K - sh.t + sh.g * sh.t);
+                cudaError_t e = bs_launch_one(l, bs_group_kernel<K, K - sh.t, sh.g, MB>, MB, first_kmer, n_units);
+                if (e != cudaSuccess) return e;
+                first_kmer += n_units * sh.g;
+            }
+        }
+        return bs_launch_shapes<K, S + 1>(l, first_kmer);
+    } else {
+        return cudaSuccess;
+    }
+}
+
+template <int K>
+static cudaError_t launch_bs_k(BsLaunchCtx &l) {
+    const Ctx &c = *l.c;
+    uint32_t first = 0;
+    // shapes in table order (the heaviest units first), then the k-mers that found no partner
+    cudaError_t e = bs_launch_shapes<K, 0>(l, first);
+    if (e != cudaSuccess) return e;
+    if (first < c.n_kmers) {
+        // registers: 3K of state + the row masks of two columns in flight (ptxas wants about 6K + 26);
+        // CTAs (= warps) per SM chosen so that nothing spills
+        constexpr int MB = bs_warps_per_sm_c(K);
+        e = bs_launch_one(l, bs_scan_kernel<K, MB>, MB, first, c.n_kmers - first);
+    }
+    return e;
+}
+
+} // namespace apc

@@ -285,13 +285,9 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
     r.n_tiles = (uint32_t)((count + kTileReads - 1) / kTileReads);
     r.n_reads = count;
     if (c.variant.bitslice()) {
-        // a job is one k-mer x sg_per_job super-groups (1024 reads each) for one warp
-        uint32_t spj = (uint32_t)c.opt_tiles_per_job;
-        if (spj == 0) {
-            const uint64_t warps = (uint64_t)c.sm_count * bs_warps_per_sm(c.k);
-            const uint64_t jobs1 = ((count + 1023) / 1024) * c.n_kmers;
-            spj = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(1, jobs1 / (warps * 128)));
-        }
+        // a job is one unit (one or several k-mers) x sg_per_job super-groups (1024 reads each) for one warp;
+        // 0 = chosen per launch (bitslice_core.cuh)
+        const uint32_t spj = (uint32_t)c.opt_tiles_per_job;
         return launch_bs_scan(c, first, first + count, d_counts, spj, launches);
     }
 

@@ -150,8 +150,27 @@ uint64_t apc_last_scan_launches(const apc_ctx *ctx);
  * k-mer per 32-bit word, 2 = two per word (k<=16), 3 = three per word
  * (k<=10), 6 = three per 64-bit pair (k<=21).  "tiles_per_job": work per job
  * of the persistent warps (0 auto): 32-read tiles for the row-packed
- * kernels, 1024-read super-groups for the bit-sliced one. */
+ * kernels, 1024-read super-groups for the bit-sliced one.  "shape_mask": the
+ * unit shapes the default kernel may group k-mers into (bit s = shape s of
+ * apc_plan_queries; default all, 0 = one k-mer per warp), applied at the next
+ * apc_set_queries. */
 int apc_set_option(apc_ctx *ctx, const char *name, int64_t value);
+
+/* The scan plan apc_set_queries would build for these k-mers (needs no GPU):
+ * the default kernel scans k-mers that share a prefix — or, walking the text
+ * backwards, a suffix — in units whose common rows are computed once.
+ * order_out[n_kmers] = the k-mer indices in scan order (units of shape 0, 1,
+ * ..., then the ungrouped k-mers), reversed_out[n_kmers] = 1 where the k-mer
+ * at that position is scanned reversed, units_out[APC_PLAN_SHAPES] = units per
+ * shape, shape_t_out / shape_g_out[APC_PLAN_SHAPES] = private bases per member
+ * and members per unit of each shape for this k (0 where the shape does not
+ * exist).  Any output pointer may be NULL.  Introspection for tests and
+ * tuning; the counts do not depend on the plan. */
+#define APC_PLAN_SHAPES 8
+int apc_plan_queries(uint8_t k, const uint64_t *kmers, uint32_t n_kmers,
+                     uint32_t *order_out, uint8_t *reversed_out,
+                     uint32_t *units_out, int32_t *shape_t_out,
+                     int32_t *shape_g_out);
 
 /* Integer-pipe peak microbenchmark (roofline denominator):
  * runs dependent-free LOP3 / IMAD / mixed chains on every SM and returns
