@@ -36,7 +36,12 @@ __device__ __forceinline__ BsCarry bs_carry_init() {
 
 // N consecutive rows of one text column, the first of them being row FIRST of the k-mer: e_i
 // from the warp's mask slot (LDS with a uniform-register offset), then the five LOP3 of the row.
-template <int N, int FIRST>
+// HIT: the last of the N rows is row k-1, the row whose bits are the hits.  It is made sticky —
+// each level keeps every bit it ever had — so that at the end of a read it holds "level e was
+// reached in SOME column" and no separate accumulators are needed.  Because the levels are nested
+// (R0 <= R1 <= R2, also with the sticky bits), OR-ing in the old value of the same level subsumes
+// the insertion term (the old value of the level below): the sticky row costs the same five LOP3.
+template <int N, int FIRST, bool HIT>
 __device__ __forceinline__ void bs_rows(uint32_t (&r0)[N], uint32_t (&r1)[N], uint32_t (&r2)[N], BsCarry &c,
                                         const char *slot_lane, const uint32_t (&off)[N]) {
     const uint32_t ALL = 0xFFFFFFFFu;
@@ -45,10 +50,17 @@ __device__ __forceinline__ void bs_rows(uint32_t (&r0)[N], uint32_t (&r1)[N], ui
         const int i = FIRST + j;
         const uint32_t e = *reinterpret_cast<const uint32_t *>(slot_lane + off[j]);
         const uint32_t o0 = r0[j], o1 = r1[j], o2 = r2[j];
-        const uint32_t n0 = i < 1 ? e : and2(c.p0, e);
-        // rows 0 (level 1) and 0..1 (level 2) always match: that many k-mer bases can be skipped
-        const uint32_t n1 = i < 1 ? ALL : or3(and_or(c.p1, e, o0), c.p0, c.n0p);
-        const uint32_t n2 = i < 2 ? ALL : or3(and_or(c.p2, e, o1), c.p1, c.n1p);
+        uint32_t n0, n1, n2;
+        if (HIT && j == N - 1) {
+            n0 = i < 1 ? (e | o0) : and_or(c.p0, e, o0);
+            n1 = i < 1 ? ALL : or3(and_or(c.p1, e, o1), c.p0, c.n0p);
+            n2 = i < 2 ? ALL : or3(and_or(c.p2, e, o2), c.p1, c.n1p);
+        } else {
+            n0 = i < 1 ? e : and2(c.p0, e);
+            // rows 0 (level 1) and 0..1 (level 2) always match: that many k-mer bases can be skipped
+            n1 = i < 1 ? ALL : or3(and_or(c.p1, e, o0), c.p0, c.n0p);
+            n2 = i < 2 ? ALL : or3(and_or(c.p2, e, o1), c.p1, c.n1p);
+        }
         r0[j] = n0; r1[j] = n1; r2[j] = n2;
         c.p0 = o0; c.p1 = o1; c.p2 = o2;
         c.n0p = n0; c.n1p = n1;
@@ -102,7 +114,6 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
                unsigned int *__restrict__ job_counter) {
     __shared__ __align__(16) uint32_t s_mask[2][4 * kGroupsPerSuper];
     const uint32_t lane = threadIdx.x;
-    const uint32_t ALL = 0xFFFFFFFFu;
     const uint32_t pairs = (read_len + 1) / 2; // an odd length is rounded up with one padding column (N: matches nothing)
 
     for (;;) {
@@ -119,7 +130,6 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
         for (uint32_t sg = jb * sg_per_job; sg < sg_end; sg++) {
             uint32_t r0[K], r1[K], r2[K];
             bs_rows_init<K, 0>(r0, r1, r2);
-            uint32_t a0 = 0, a1 = K <= 1 ? ALL : 0, a2 = K <= 2 ? ALL : 0;
             const uint4 *p = planes + ((size_t)(sg_first + sg) * cols) * kGroupsPerSuper + lane;
             uint4 ma = __ldg(p), mb = __ldg(p + kGroupsPerSuper);
             for (uint32_t pr = 0; pr < pairs; pr++) {
@@ -127,19 +137,15 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
                 const uint4 na = __ldg(p), nb = __ldg(p + kGroupsPerSuper); // buffer is padded by two columns
                 APC_BS_STAGE_MASKS()
                 BsCarry c = bs_carry_init();
-                bs_rows<K, 0>(r0, r1, r2, c, reinterpret_cast<const char *>(s_mask[0]) + lane * 4, off);
-                const uint32_t h0 = r0[K - 1], h1 = r1[K - 1], h2 = r2[K - 1];
+                bs_rows<K, 0, true>(r0, r1, r2, c, reinterpret_cast<const char *>(s_mask[0]) + lane * 4, off);
                 c = bs_carry_init();
-                bs_rows<K, 0>(r0, r1, r2, c, reinterpret_cast<const char *>(s_mask[1]) + lane * 4, off);
-                a0 = or3(a0, h0, r0[K - 1]);
-                a1 = or3(a1, h1, r1[K - 1]);
-                a2 = or3(a2, h2, r2[K - 1]);
+                bs_rows<K, 0, true>(r0, r1, r2, c, reinterpret_cast<const char *>(s_mask[1]) + lane * 4, off);
                 ma = na; mb = nb;
             }
-            // hits of these 32 reads: [d<=0] + [d<=1] + [d<=2] (:589-593), reads outside the
-            // scanned range (padding of the last group, or a sub-range scan) masked out
+            // hits of these 32 reads: [d<=0] + [d<=1] + [d<=2] (:589-593) = the sticky row k-1; reads outside
+            // the scanned range (padding of the last group, or a sub-range scan) masked out
             const uint32_t vm = bs_valid_mask(((uint64_t)(sg_first + sg) * kGroupsPerSuper + lane) * 32, range_lo, range_hi);
-            cnt += __popc(a0 & vm) + __popc(a1 & vm) + __popc(a2 & vm);
+            cnt += __popc(r0[K - 1] & vm) + __popc(r1[K - 1] & vm) + __popc(r2[K - 1] & vm);
         }
         const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, cnt);
         if (lane == 0 && total) atomicAdd(&counts[__ldg(perm + u)], (unsigned long long)total);
@@ -193,45 +199,33 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
         for (int g = 0; g < G; g++) cnt[g] = 0;
         const uint32_t sg_end = min(n_sg, (jb + 1) * sg_per_job);
         for (uint32_t sg = jb * sg_per_job; sg < sg_end; sg++) {
-            uint32_t s0[P], s1[P], s2[P], x0[G][T], x1[G][T], x2[G][T], a0[G], a1[G], a2[G];
+            uint32_t s0[P], s1[P], s2[P], x0[G][T], x1[G][T], x2[G][T];
             bs_rows_init<P, 0>(s0, s1, s2);
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                bs_rows_init<T, P>(x0[g], x1[g], x2[g]);
-                a0[g] = a1[g] = a2[g] = 0;
-            }
+            for (int g = 0; g < G; g++) bs_rows_init<T, P>(x0[g], x1[g], x2[g]);
             const uint4 *p = planes + ((size_t)(sg_first + sg) * cols + col0) * kGroupsPerSuper + lane;
             uint4 ma = __ldg(p), mb = __ldg(p + cstep);
             for (uint32_t pr = 0; pr < pairs; pr++) {
                 p += 2 * cstep;
                 const uint4 na = __ldg(p), nb = __ldg(p + cstep); // the buffer is padded by two columns at both ends
                 APC_BS_STAGE_MASKS()
-                uint32_t h0[G], h1[G], h2[G];
 #pragma unroll
                 for (int col = 0; col < 2; col++) {
                     const char *slot = reinterpret_cast<const char *>(s_mask[col]) + lane * 4;
                     BsCarry c = bs_carry_init();
-                    bs_rows<P, 0>(s0, s1, s2, c, slot, off_s);
+                    bs_rows<P, 0, false>(s0, s1, s2, c, slot, off_s);
 #pragma unroll
                     for (int g = 0; g < G; g++) {
                         BsCarry cg = c;
-                        bs_rows<T, P>(x0[g], x1[g], x2[g], cg, slot, off_t[g]);
-                        if (col == 0) {
-                            h0[g] = x0[g][T - 1]; h1[g] = x1[g][T - 1]; h2[g] = x2[g][T - 1];
-                        }
+                        bs_rows<T, P, true>(x0[g], x1[g], x2[g], cg, slot, off_t[g]);
                     }
-                }
-#pragma unroll
-                for (int g = 0; g < G; g++) {
-                    a0[g] = or3(a0[g], h0[g], x0[g][T - 1]);
-                    a1[g] = or3(a1[g], h1[g], x1[g][T - 1]);
-                    a2[g] = or3(a2[g], h2[g], x2[g][T - 1]);
                 }
                 ma = na; mb = nb;
             }
             const uint32_t vm = bs_valid_mask(((uint64_t)(sg_first + sg) * kGroupsPerSuper + lane) * 32, range_lo, range_hi);
 #pragma unroll
-            for (int g = 0; g < G; g++) cnt[g] += __popc(a0[g] & vm) + __popc(a1[g] & vm) + __popc(a2[g] & vm);
+            for (int g = 0; g < G; g++) // the sticky last row of each tail holds the hits
+                cnt[g] += __popc(x0[g][T - 1] & vm) + __popc(x1[g][T - 1] & vm) + __popc(x2[g][T - 1] & vm);
         }
 #pragma unroll
         for (int g = 0; g < G; g++) {
