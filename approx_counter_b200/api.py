@@ -196,6 +196,9 @@ def device_count():
     return max(0, n)
 
 
+PLAN_SHAPES = 12  # APC_PLAN_SHAPES (include/apc.h)
+
+
 def plan_queries(kmers, k):
     """The scan plan of the default kernel for these k-mers (apc_plan_queries; needs no GPU):
     dict(order, reversed, units, shape_t, shape_g) — see include/apc.h."""
@@ -204,9 +207,9 @@ def plan_queries(kmers, k):
     n = len(km)
     order = np.zeros(n, np.uint32)
     rev = np.zeros(n, np.uint8)
-    units = np.zeros(8, np.uint32)
-    st = np.zeros(8, np.int32)
-    sg = np.zeros(8, np.int32)
+    units = np.zeros(PLAN_SHAPES, np.uint32)
+    st = np.zeros(PLAN_SHAPES, np.int32)
+    sg = np.zeros(PLAN_SHAPES, np.int32)
     rc = lib.apc_plan_queries(int(k), km.ctypes.data, n, order.ctypes.data, rev.ctypes.data, units.ctypes.data,
                               st.ctypes.data, sg.ctypes.data)
     if rc != 0:

@@ -36,10 +36,10 @@ constexpr int kScanWarps = 8;      // warps per CTA of the scan kernel
 struct BsShape {
     int t, g;
 };
-constexpr int kBsShapes = 8;
+constexpr int kBsShapes = 12;
 constexpr int kBsMaxRows = 48;
 constexpr BsShape bs_shape(int k, int s) {
-    const BsShape table[kBsShapes] = {{5, 6}, {8, 4}, {6, 3}, {2, 8}, {3, 6}, {3, 4}, {1, 4}, {k - k / 2, 2}};
+    const BsShape table[kBsShapes] = {{2, 16}, {6, 6}, {5, 6}, {8, 4}, {2, 12}, {3, 8}, {6, 3}, {2, 8}, {3, 6}, {3, 4}, {1, 4}, {k - k / 2, 2}};
     const BsShape sh = table[s];
     const int p = k - sh.t;
     if (p < 2 || sh.t < 1 || p + sh.g * sh.t > kBsMaxRows) return BsShape{0, 0};

@@ -88,10 +88,11 @@ uint64_t bs_reverse_kmer(uint64_t kmer, int k) { // base order reversed (NOT com
 
 namespace {
 
-// Estimated cost of a unit in row-equivalents (one row = 5 LOP3 per column and 32 reads): its rows plus
-// the per-column work that does not depend on the rows (plane loads, mask staging, loop) and the hit
-// accumulation of each member.
-inline float bs_unit_cost(int rows, int g) { return (float)rows + 1.0f + 0.3f * (float)g; }
+// Estimated cost of a unit in row-equivalents (one row = 5 LOP3 per column and 32 reads).  Measured
+// (tools/shape_bench.py, profiles/r01_shape_bench.jsonl): the time of a unit is proportional to its rows
+// whatever the shape (0.175 us per row and 1024 reads x 100 columns), plus about half a row for a grouped unit
+// (fewer resident warps than the one-k-mer kernel).
+inline float bs_unit_cost(int rows, int g) { return (float)rows + (g > 1 ? 0.5f : 0.f); }
 
 struct BsGroup {
     uint32_t first; // position in the sorted array

@@ -242,7 +242,7 @@ def test_prefix_sharing_kmers_are_paired_correctly(counter, k):
             counter.set_option("scan_variant", 0)
         assert np.array_equal(got, want), variant
         if variant == 0:
-            assert 2 <= t["scan_launches"] <= 9  # one launch per unit shape in use + the ungrouped k-mers
+            assert 2 <= t["scan_launches"] <= 13  # one launch per unit shape in use + the ungrouped k-mers
 
 
 @pytest.mark.parametrize("k", range(3, 33))

@@ -32,7 +32,7 @@ def check_plan(kmers, k):
     n = len(kmers)
     assert sorted(p["order"].tolist()) == list(range(n))          # a permutation: every k-mer scanned exactly once
     at = 0
-    for s in range(8):
+    for s in range(len(p["units"])):
         t, g = int(p["shape_t"][s]), int(p["shape_g"][s])
         if g == 0:
             assert p["units"][s] == 0

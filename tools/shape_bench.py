@@ -43,7 +43,7 @@ if __name__ == "__main__":
             c.set_option("shape_mask", 0)
             t1 = time_scan(c, singles, k) / len(singles)
             print(json.dumps({"k": k, "shape": "single", "rows": k, "us_per_unit": round(t1 * 1e3, 3)}), flush=True)
-            for s in range(8):
+            for s in range(len(shapes["units"])):
                 t, g = int(shapes["shape_t"][s]), int(shapes["shape_g"][s])
                 if g == 0:
                     continue
