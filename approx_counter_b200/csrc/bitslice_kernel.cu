@@ -81,9 +81,12 @@ cudaError_t launch_build_planes(const Ctx &c) {
 
 // ---- host side of the grouping ---------------------------------------------------------------------
 uint64_t bs_reverse_kmer(uint64_t kmer, int k) { // base order reversed (NOT complemented)
-    uint64_t r = 0;
-    for (int i = 0; i < k; i++) r = (r << 2) | ((kmer >> (2 * i)) & 3u);
-    return r;
+    // swap the 2-bit groups of the word end for end, then drop the 32 - k unused groups
+    uint64_t r = kmer;
+    r = ((r >> 2) & 0x3333333333333333ull) | ((r & 0x3333333333333333ull) << 2);
+    r = ((r >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((r & 0x0F0F0F0F0F0F0F0Full) << 4);
+    r = __builtin_bswap64(r);
+    return r >> (64 - 2 * k);
 }
 
 namespace {
@@ -99,53 +102,90 @@ struct BsGroup {
     int shape;      // -1 = single
 };
 
-// Cheapest cover of the sorted k-mers v[0..n) by units (runs of g neighbours whose common prefix has at
-// least k - t bases) and singles.  cost_per[i] = share of k-mer i in its unit's cost.
-void bs_cover(const std::vector<uint64_t> &v, int k, uint32_t shape_mask, std::vector<BsGroup> &groups,
-              std::vector<float> *cost_per) {
-    const size_t n = v.size();
-    std::vector<float> f(n + 1, 0.f);
-    std::vector<int8_t> choice(n + 1, -1);
-    BsShape shapes[kBsShapes];
-    float shape_cost[kBsShapes];
-    for (int s = 0; s < kBsShapes; s++) {
-        shapes[s] = (shape_mask >> s) & 1u ? bs_shape(k, s) : BsShape{0, 0};
-        shape_cost[s] = shapes[s].g ? bs_unit_cost(k - shapes[s].t + shapes[s].g * shapes[s].t, shapes[s].g) : 0.f;
-    }
-    const float single = bs_unit_cost(k, 1);
-    for (size_t i = 1; i <= n; i++) {
-        f[i] = f[i - 1] + single;
-        choice[i] = -1;
+struct BsShapeSet { // the shapes available for this k, most members first
+    int n = 0, max_t = 0;
+    int id[kBsShapes], g[kBsShapes], shift[kBsShapes];
+    float cost[kBsShapes];
+    float single = 0.f;
+    BsShapeSet(int k, uint32_t shape_mask) {
         for (int s = 0; s < kBsShapes; s++) {
-            const int g = shapes[s].g;
-            if (g == 0 || (size_t)g > i) continue;
-            // sorted: the first and the last of the run share the prefix, so all in between do
-            if (((v[i - g] ^ v[i - 1]) >> (2 * shapes[s].t)) != 0) continue;
-            const float c = f[i - g] + shape_cost[s];
-            if (c < f[i]) {
-                f[i] = c;
-                choice[i] = (int8_t)s;
+            const BsShape sh = (shape_mask >> s) & 1u ? bs_shape(k, s) : BsShape{0, 0};
+            if (!sh.g) continue;
+            id[n] = s;
+            g[n] = sh.g;
+            shift[n] = 2 * sh.t;
+            cost[n] = bs_unit_cost(k - sh.t + sh.g * sh.t, sh.g);
+            max_t = std::max(max_t, sh.t);
+            n++;
+        }
+        single = bs_unit_cost(k, 1);
+    }
+};
+
+// Cheapest cover of the sorted k-mers v[0..n) by units (runs of g neighbours whose common prefix has at
+// least k - t bases) and singles.
+void bs_cover(const uint64_t *v, size_t n, const BsShapeSet &ss, std::vector<float> &f, std::vector<int8_t> &choice,
+              std::vector<BsGroup> &groups) {
+    f.resize(n + 1);
+    choice.resize(n + 1);
+    f[0] = 0.f;
+    const int max_shift = std::min(2 * ss.max_t, 63);
+    for (size_t i = 1; i <= n; i++) {
+        float best = f[i - 1] + ss.single;
+        int8_t pick = -1;
+        // no shape fits unless the last two of the run share at least k - max_t bases
+        if (i >= 2 && ((v[i - 2] ^ v[i - 1]) >> max_shift) == 0) {
+            for (int s = 0; s < ss.n; s++) {
+                const size_t g = (size_t)ss.g[s];
+                if (g > i) continue;
+                // sorted: the first and the last of the run share the prefix, so all in between do
+                if (((v[i - g] ^ v[i - 1]) >> ss.shift[s]) != 0) continue;
+                const float c = f[i - g] + ss.cost[s];
+                if (c < best) {
+                    best = c;
+                    pick = (int8_t)s;
+                }
             }
         }
+        f[i] = best;
+        choice[i] = pick;
     }
     groups.clear();
-    if (cost_per) cost_per->assign(n, single);
     for (size_t i = n; i > 0;) {
         const int s = choice[i];
-        const int g = s < 0 ? 1 : shapes[s].g;
-        groups.push_back(BsGroup{(uint32_t)(i - g), s});
-        if (cost_per && s >= 0)
-            for (size_t j = i - g; j < i; j++) (*cost_per)[j] = shape_cost[s] / (float)g;
+        const size_t g = s < 0 ? 1 : (size_t)ss.g[s];
+        groups.push_back(BsGroup{(uint32_t)(i - g), s < 0 ? -1 : ss.id[s]});
         i -= g;
     }
     std::reverse(groups.begin(), groups.end());
+}
+
+struct BsKey {
+    uint64_t v;
+    uint32_t i;
+};
+
+// Stable LSD radix sort by v over its 2k significant bits (the keys arrive in index order, so equal
+// k-mers stay in index order): the comparison sort was most of the planning time at lim = 10 000.
+void bs_sort_keys(std::vector<BsKey> &a, std::vector<BsKey> &tmp, int k) {
+    const size_t n = a.size();
+    tmp.resize(n);
+    BsKey *src = a.data(), *dst = tmp.data();
+    for (int shift = 0; shift < 2 * k; shift += 8) {
+        size_t count[257] = {0};
+        for (size_t i = 0; i < n; i++) count[((src[i].v >> shift) & 0xFFu) + 1]++;
+        for (int b = 0; b < 256; b++) count[b + 1] += count[b];
+        for (size_t i = 0; i < n; i++) dst[count[(src[i].v >> shift) & 0xFFu]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != a.data()) a.swap(tmp);
 }
 
 } // namespace
 
 // Groups the query k-mers into units.  Each k-mer is looked at forwards and reversed (suffix sharing);
 // a first cover of ALL k-mers in either direction tells which direction serves a k-mer better, then
-// each direction's k-mers are covered on their own.  order[] receives the k-mer indices in scan order
+// each direction's k-mers are covered on their own (bs_cover).  order[] receives the k-mer indices in scan order
 // (units of shape 0, 1, ..., then singles), reversed[] whether the k-mer at that position is to be
 // stored reversed, units[s] the number of units of shape s.  shape_mask: the shapes that may be used.
 void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_mask, std::vector<uint32_t> &order,
@@ -155,77 +195,71 @@ void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_m
     reversed.assign(n, 0);
     for (auto &u : units) u = 0;
     if (!shape_mask || k < 3 || n < 2) return;
+    const BsShapeSet ss(k, shape_mask);
+    if (ss.n == 0) return;
 
-    std::vector<uint64_t> val[2];
-    std::vector<uint32_t> idx[2]; // sorted position -> caller's index
-    std::vector<float> cost[2];   // by caller's index
+    std::vector<BsKey> sorted[2], tmp;
+    std::vector<float> share[2]; // by caller's index: the k-mer's share of its unit's cost when ALL k-mers go in direction d
     std::vector<BsGroup> groups;
+    std::vector<uint64_t> vals(n);
+    std::vector<float> f;
+    std::vector<int8_t> choice;
     for (int d = 0; d < 2; d++) {
-        idx[d] = order;
-        std::vector<uint64_t> key(n);
-        for (uint32_t i = 0; i < n; i++) key[i] = d ? bs_reverse_kmer(kmers[i], k) : kmers[i];
-        std::sort(idx[d].begin(), idx[d].end(),
-                  [&](uint32_t a, uint32_t b) { return key[a] != key[b] ? key[a] < key[b] : a < b; });
-        val[d].resize(n);
-        for (uint32_t i = 0; i < n; i++) val[d][i] = key[idx[d][i]];
-        std::vector<float> per;
-        bs_cover(val[d], k, shape_mask, groups, &per);
-        cost[d].resize(n);
-        for (uint32_t i = 0; i < n; i++) cost[d][idx[d][i]] = per[i];
+        sorted[d].resize(n);
+        for (uint32_t i = 0; i < n; i++) sorted[d][i] = BsKey{d ? bs_reverse_kmer(kmers[i], k) : kmers[i], i};
+        bs_sort_keys(sorted[d], tmp, k);
+        for (uint32_t i = 0; i < n; i++) vals[i] = sorted[d][i].v;
+        bs_cover(vals.data(), n, ss, f, choice, groups);
+        share[d].resize(n);
+        for (const BsGroup &grp : groups) {
+            const int g = grp.shape < 0 ? 1 : bs_shape(k, grp.shape).g;
+            const float c = (f[grp.first + g] - f[grp.first]) / (float)g;
+            for (int j = 0; j < g; j++) share[d][sorted[d][grp.first + j].i] = c;
+        }
     }
-    std::vector<uint8_t> side(n);
-    for (uint32_t i = 0; i < n; i++) side[i] = cost[1][i] < cost[0][i] ? 1 : 0;
 
-    // cover each side; k-mers left single on their side but grouped on the other one in the first
-    // cover change sides once
+    // each k-mer goes to the direction in which it was cheaper, then each direction is covered on its own
     std::vector<uint64_t> sv[2];
     std::vector<uint32_t> si[2];
     std::vector<BsGroup> sg[2];
-    const float single = bs_unit_cost(k, 1);
-    for (int round = 0; round < 2; round++) {
-        for (int d = 0; d < 2; d++) {
-            sv[d].clear();
-            si[d].clear();
-            for (uint32_t i = 0; i < n; i++)
-                if (side[idx[d][i]] == d) {
-                    sv[d].push_back(val[d][i]);
-                    si[d].push_back(idx[d][i]);
-                }
-            bs_cover(sv[d], k, shape_mask, sg[d], nullptr);
+    for (int d = 0; d < 2; d++) {
+        sv[d].reserve(n);
+        si[d].reserve(n);
+        for (uint32_t i = 0; i < n; i++) {
+            const uint32_t q = sorted[d][i].i;
+            if ((share[1][q] < share[0][q] ? 1 : 0) == d) {
+                sv[d].push_back(sorted[d][i].v);
+                si[d].push_back(q);
+            }
         }
-        if (round == 1) break;
-        uint32_t moved = 0;
-        for (int d = 0; d < 2; d++)
-            for (const BsGroup &g : sg[d])
-                if (g.shape < 0 && cost[1 - d][si[d][g.first]] < single) {
-                    side[si[d][g.first]] = (uint8_t)(1 - d);
-                    moved++;
-                }
-        if (!moved) break;
+        bs_cover(sv[d].data(), sv[d].size(), ss, f, choice, sg[d]);
     }
 
     // scan order: shape by shape, forward units then backward units, then the singles (stored forwards)
     uint32_t at = 0;
-    for (int s = 0; s < kBsShapes; s++) {
-        const int g = bs_shape(k, s).g;
-        for (int d = 0; d < 2; d++)
-            for (const BsGroup &grp : sg[d]) {
-                if (grp.shape != s) continue;
-                for (int j = 0; j < g; j++) {
-                    order[at] = si[d][grp.first + j];
-                    reversed[at] = (uint8_t)d;
-                    at++;
-                }
-                units[s]++;
+    std::vector<uint32_t> start(kBsShapes + 1, 0); // first position of each shape's members, singles last
+    for (int d = 0; d < 2; d++)
+        for (const BsGroup &grp : sg[d]) {
+            if (grp.shape >= 0) {
+                units[grp.shape]++;
+                start[grp.shape] += (uint32_t)bs_shape(k, grp.shape).g;
             }
+        }
+    for (int s = 0; s <= kBsShapes; s++) {
+        const uint32_t members = s < kBsShapes ? start[s] : 0;
+        start[s] = at;
+        at += members;
     }
     for (int d = 0; d < 2; d++)
-        for (const BsGroup &grp : sg[d])
-            if (grp.shape < 0) {
-                order[at] = si[d][grp.first];
-                reversed[at] = 0;
-                at++;
+        for (const BsGroup &grp : sg[d]) {
+            const int s = grp.shape < 0 ? kBsShapes : grp.shape;
+            const int g = grp.shape < 0 ? 1 : bs_shape(k, grp.shape).g;
+            for (int j = 0; j < g; j++) {
+                order[start[s]] = si[d][grp.first + j];
+                reversed[start[s]] = (uint8_t)(grp.shape < 0 ? 0 : d);
+                start[s]++;
             }
+        }
 }
 
 // ---- dispatch ------------------------------------------------------------------------------------------
