@@ -473,13 +473,33 @@ def run_b200(args, w):
     # + the k-mers and the counts
     cols_padded = ((sl + 1 + 15) // 16) * 16
     hbm_bytes_launch = ((n + 1023) // 1024) * 32 * cols_padded * 16 + 16 * q_start
+    # What the ALU pipe really executes: the scan plan groups k-mers into units whose shared rows are
+    # computed once; every row of a unit costs 5 LOP3 per column and 32 reads (bitslice_core.cuh).
+    from approx_counter_b200 import plan_queries
+    plan_rows, plan_units, plan_reversed = [], [], []
+    for q in queries:
+        pl = plan_queries(q, k)
+        rows = sum(int(u) * (k - int(t) + int(g) * int(t)) for u, t, g in zip(pl["units"], pl["shape_t"], pl["shape_g"]))
+        rows += (len(q) - int((pl["units"] * pl["shape_g"]).sum())) * k
+        plan_rows.append(rows)
+        plan_units.append([int(u) for u in pl["units"]])
+        plan_reversed.append(int(pl["reversed"].sum()))
+    n_sg_rank = (n + 1023) // 1024
+    lop3_lane_ops = sum(5.0 * rows * n_sg_rank * 1024 * (2 * ((L + 1) // 2)) for rows, L in zip(plan_rows, (sl, sl + 1)))
+    executed = lop3_lane_ops / (kern_ms / 1e3 / max(args.steps, 1))
     roofline = {
-        "bound": "int-alu", "kernel": "bs_group_kernel<G=4>, bs_group_kernel<G=2>, bs_scan_kernel (one scan = up to three launches)", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
+        "bound": "int-alu", "kernel": "bs_group_kernel<K,P,G> (one launch per unit shape in use) + bs_scan_kernel<K> (ungrouped k-mers); "
+                                      "one scan = up to 13 concurrent launches", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
         "unit": "Tint-op/s", "frac": achieved / alu_peak, "traffic": traffic, "ncu_alu_pipe_pct": ncu_alu,
         "peak_source": f"ALU pipe nominal = {sms} SM x 4 SMSP x 16 lanes/clk x {sm_max:.0f} MHz (SURVEY.md §8d)",
         "algorithmic_ops_per_column": ALGO_OPS_PER_COLUMN, "columns_per_launch": cols_launch,
         "avg_launch_ms": per_launch_s * 1e3, "scans_timed": n_scans, "launches_timed": n_launch,
         "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
+        "executed": {"lop3_Tlane_ops_per_s": executed / 1e12, "frac_of_alu_peak": executed / alu_peak,
+                     "rows_per_scan": plan_rows, "rows_if_one_kmer_per_warp": [len(q) * k for q in queries],
+                     "units_per_shape": plan_units, "kmers_scanned_backwards": plan_reversed,
+                     "note": "LOP3 the plan executes (5 per unit row, column and 32 reads) / time: the utilisation "
+                             "figure that cannot exceed 1; `frac` above is against the ALGORITHMIC 16 ops per column"},
         "measured_int_peaks_Tops": {kk: v / 1e12 for kk, v in int_peak.items()},
         "frac_of_measured_lop3_peak": achieved / int_peak["lop3_ops_per_s"],
         "hbm": {"algorithmic_bytes_per_launch": hbm_bytes_launch,
