@@ -18,10 +18,11 @@ _u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
 def build(force=False):
     """Compile the oracle with its Makefile (gcc/g++, seconds)."""
     need = force or not all(
-        os.path.exists(os.path.join(_HERE, f)) for f in ("liborc.so", "libseqan_model.so"))
+        os.path.exists(os.path.join(_HERE, f)) for f in ("liborc.so", "libseqan_model.so", "libfm_index_model.so"))
     if not need:
         for so, srcs in (("liborc.so", ("apc_oracle.c", "apc_oracle.h")),
-                         ("libseqan_model.so", ("seqan_model.cpp",))):
+                         ("libseqan_model.so", ("seqan_model.cpp",)),
+                         ("libfm_index_model.so", ("fm_index_model.cpp",))):
             t = os.path.getmtime(os.path.join(_HERE, so))
             need |= any(os.path.getmtime(os.path.join(_HERE, s)) > t for s in srcs)
     if need:
@@ -30,6 +31,7 @@ def build(force=False):
 
 _lib = None
 _model = None
+_fm = None
 
 
 def lib():
@@ -86,6 +88,18 @@ def model():
                                               C.c_uint8, C.c_int, _u64p, C.c_void_p]
         _model = M
     return _model
+
+
+def fm():
+    global _fm
+    if _fm is None:
+        build()
+        F = C.CDLL(os.path.join(_HERE, "libfm_index_model.so"))
+        F.fm_error_count.restype = C.c_int
+        F.fm_error_count.argtypes = [_u8p, _u64p, C.c_uint64, _u64p, C.c_uint64, C.c_uint8, C.c_int, _u64p,
+                                     C.POINTER(C.c_double)]
+        _fm = F
+    return _fm
 
 
 _CODE = np.full(256, 4, np.uint8)
@@ -193,6 +207,19 @@ def seqan_model_error_count(codes, offs, kmers, k, variant=0, want_flags=False):
     model().seqan_model_error_count(codes, offs, n, kmers, len(kmers), k, variant, out,
                                     None if flags is None else flags.ctypes.data)
     return (out, flags) if want_flags else out
+
+
+def fm_index_error_count(codes, offs, kmers, k, nb_thread=0, want_seconds=False):
+    """errorCount the way the reference runs it (:531-601): build a bidirectional FM index of the reads, search
+    every k-mer with the optimal-search-scheme recursion (fm_index_model.cpp).  want_seconds: also return
+    (index build s, search s)."""
+    kmers = np.ascontiguousarray(kmers, np.uint64)
+    out = np.zeros(len(kmers), np.uint64)
+    sec = (C.c_double * 2)()
+    rc = fm().fm_error_count(codes, offs, len(offs) - 1, kmers, len(kmers), k, nb_thread, out, sec)
+    if rc != 0:
+        raise ValueError("fm_error_count: text too long for 32-bit positions or k outside [4,32]")
+    return (out, (sec[0], sec[1])) if want_seconds else out
 
 
 def sample_sequences(codes, offs, perm, nb_sample, cut, bot):

@@ -88,6 +88,8 @@ def test_closed_form_equals_seqan_model(k, variant):
         got = orc.seqan_model_error_count(codes, offs, kmers, k, variant=variant)
         assert np.array_equal(got, want), (k, trial, reads)
         assert np.array_equal(orc.error_count(codes, offs, kmers, k, fast=True), want)
+        if variant == 0:  # the same recursion over the bidirectional FM index (the index-based CPU baseline)
+            assert np.array_equal(orc.fm_index_error_count(codes, offs, kmers, k), want), (k, trial, reads)
 
 
 def test_count_invariants():
@@ -215,3 +217,45 @@ def test_closed_form_equals_seqan_model_on_workloads(built, n, sl, k, lim, seed,
         if k <= 20:  # the planted adapters (28 / 22 bases) are shorter than k = 32: only exact hits there
             assert (flags[:, 1, :] & ~flags[:, 0, :].astype(bool)).sum() > 0
             assert (flags[:, 2, :] & ~flags[:, 1, :].astype(bool)).sum() > 0
+
+
+@pytest.mark.parametrize("n,sl,k,lim,seed", [(20000, 100, 16, 500, 1002), (8000, 150, 20, 400, 1003),
+                                             (6000, 200, 32, 300, 1004), (12000, 60, 10, 300, 1005)])
+def test_fm_index_model_equals_closed_form_at_scale(built, n, sl, k, lim, seed):
+    """errorCount as the reference runs it — a bidirectional FM index of the sampled read
+    ends searched with the literal optimal-search-scheme recursion (oracle/fm_index_model.cpp) — against the
+    closed form (Myers scan) on BASELINE-like workloads, both ends, at sizes the occurrence-list model cannot
+    reach: an independent second oracle."""
+    from approx_counter_b200 import host
+    thr = orc.adjust_threshold(1.0, 16, k)
+    for bot in (False, True):
+        sample = host.synth_ends(seed, 0, n, sl, bot)
+        codes, offs = orc.encode_matrix(sample)
+        keys, cnts, _ = orc.count_kmers(codes, offs, k, thr)
+        top, _ = orc.get_most_frequent(keys, cnts, lim, k)
+        rng = np.random.default_rng(seed)
+        extra = np.array([int.from_bytes(rng.bytes(8), "little") & ((1 << (2 * k)) - 1) for _ in range(20)], np.uint64)
+        kmers = np.concatenate([top, extra])
+        want = orc.error_count(codes, offs, kmers, k, fast=True)
+        got, (t_build, t_search) = orc.fm_index_error_count(codes, offs, kmers, k, want_seconds=True)
+        assert np.array_equal(got, want)
+        assert want.max() >= 3 and t_build > 0 and t_search > 0
+        if k <= 20:
+            assert want.max() > n // 2   # adapter k-mers hit most reads (k = 32 is longer than the planted adapters)
+
+
+def test_fm_index_model_ragged_and_degenerate():
+    rng = np.random.default_rng(77)
+    reads = [b"", b"A", b"ACGTNNNNACGT", b"N" * 30, b"ACGT" * 12, b"TTTTTTTTTTTTTTTTTTTT", b"", b"ACGTACGAACGTACGT"]
+    reads += [bytes(rng.choice(ACGT, size=int(rng.integers(0, 70)))) for _ in range(200)]
+    codes, offs = orc.encode(reads)
+    for k in (4, 5, 8, 12, 16, 25, 32):
+        kmers = [orc.dna2int(("ACGT" * 8)[:k]), orc.dna2int("T" * k), 0] + \
+                [int.from_bytes(rng.bytes(8), "little") & ((1 << (2 * k)) - 1) for _ in range(5)]
+        want = orc.error_count(codes, offs, kmers, k)
+        assert np.array_equal(orc.fm_index_error_count(codes, offs, kmers, k), want), k
+        assert np.array_equal(orc.fm_index_error_count(codes, offs, kmers, k, nb_thread=1), want), k
+    codes, offs = orc.encode([])
+    assert orc.fm_index_error_count(codes, offs, [5, 6], 8).tolist() == [0, 0]
+    with pytest.raises(ValueError):
+        orc.fm_index_error_count(codes, offs, [1], 3)      # the four blocks of the scheme need k >= 4
