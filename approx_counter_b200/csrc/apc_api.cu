@@ -341,7 +341,8 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
         // index of each in the caller's order; bit 31 marks the members of a unit that is scanned backwards
         std::vector<uint32_t> order;
         std::vector<uint8_t> reversed;
-        apc::bs_group_queries(kmers, n_kmers, k, c->variant.pairing() ? c->opt_shape_mask : 0u, order, reversed, c->bs_units);
+        apc::bs_group_queries(kmers, n_kmers, k, c->variant.pairing() ? c->opt_shape_mask : 0u, (float)c->opt_alive_pct / 100.f,
+                              order, reversed, c->bs_units);
         uint64_t *hk = (uint64_t *)c->h_pinned;
         uint32_t *hp = (uint32_t *)(hk + n_kmers);
         for (uint32_t i = 0; i < n_kmers; i++) {
@@ -375,7 +376,7 @@ int apc_plan_queries(uint8_t k, const uint64_t *kmers, uint32_t n_kmers, uint32_
         std::vector<uint32_t> order;
         std::vector<uint8_t> reversed;
         uint32_t units[apc::kBsShapes];
-        apc::bs_group_queries(kmers, n_kmers, k, 0xFFFFFFFFu, order, reversed, units);
+        apc::bs_group_queries(kmers, n_kmers, k, 0xFFFFFFFFu, (float)apc::kBsAlivePct / 100.f, order, reversed, units);
         for (uint32_t i = 0; i < n_kmers; i++) {
             if (order_out) order_out[i] = order[i];
             if (reversed_out) reversed_out[i] = reversed[i];
@@ -471,6 +472,11 @@ int apc_set_option(apc_ctx *c, const char *name, int64_t value) {
     if (!std::strcmp(name, "shape_mask")) { // takes effect at the next apc_set_queries
         if (value < 0 || value > 0xFFFFFFFFll) return apc::fail(c, APC_ERR_INVALID, "shape_mask out of range");
         c->opt_shape_mask = (uint32_t)value;
+        return APC_OK;
+    }
+    if (!std::strcmp(name, "plan_alive_pct")) { // takes effect at the next apc_set_queries
+        if (value < 0 || value > 100) return apc::fail(c, APC_ERR_INVALID, "plan_alive_pct must be in [0,100]");
+        c->opt_alive_pct = (int)value;
         return APC_OK;
     }
     if (!std::strcmp(name, "scan_first_read")) {

@@ -38,6 +38,7 @@ struct BsShape {
 };
 constexpr int kBsShapes = 12;
 constexpr int kBsMaxRows = 48;
+constexpr int kBsAlivePct = 30;
 constexpr BsShape bs_shape(int k, int s) {
     const BsShape table[kBsShapes] = {{2, 16}, {6, 6}, {5, 6}, {8, 4}, {2, 12}, {3, 8}, {6, 3}, {2, 8}, {3, 6}, {3, 4}, {1, 4}, {k - k / 2, 2}};
     const BsShape sh = table[s];
@@ -46,6 +47,17 @@ constexpr BsShape bs_shape(int k, int s) {
     for (int j = 0; j < s; j++)
         if (table[j].t == sh.t && table[j].g == sh.g) return BsShape{0, 0};
     return sh;
+}
+// Rows >= bs_check_row_host(k) of a unit are computed only in the columns where something can reach them
+// (dead-row skipping, bitslice_core.cuh); k = no such split.
+constexpr int bs_check_row_host(int k) {
+#ifdef APC_BS_CHECK_ROW
+    return APC_BS_CHECK_ROW < k ? APC_BS_CHECK_ROW : k; // A/B builds (tools/build_ab.sh)
+#else
+    // A/B on the BASELINE workloads (tools/ab_skip.sh): k = 16: row 12 / 13 / 14 -> 346 / 365 / 353 kGCUPS;
+    // k = 20: 549 / 618 / 625; k = 32: 13 / 14 -> 556 / 585
+    return k >= 18 ? 14 : k >= 16 ? 13 : k;
+#endif
 }
 struct BsRange { // super-groups (1024 reads) and reads [lo, hi) of one scan
     uint32_t sg_first, n_sg;
@@ -137,6 +149,7 @@ struct Ctx {
     int opt_variant = 0;
     int opt_tiles_per_job = 0;
     uint32_t opt_shape_mask = 0xFFFFFFFFu; // unit shapes the bit-sliced scan may use (bit s = shape s of bs_shape)
+    int opt_alive_pct = kBsAlivePct;       // planner: expected share of columns in which deep rows are computed
     uint64_t opt_first_read = 0;  // scan only reads [first, first+n) of the resident sample
     int64_t opt_n_reads = -1;     // -1 = to the end
 
@@ -176,8 +189,8 @@ cudaError_t launch_scan(const Ctx &c, unsigned long long *d_counts, uint64_t *la
 cudaError_t launch_build_planes(const Ctx &c);
 cudaError_t launch_bs_scan(const Ctx &c, uint64_t read_lo, uint64_t read_hi, unsigned long long *d_counts,
                            uint32_t sg_per_job, uint64_t *launches);
-void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_mask, std::vector<uint32_t> &order,
-                      std::vector<uint8_t> &reversed, uint32_t (&units)[kBsShapes]);
+void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_mask, float alive,
+                      std::vector<uint32_t> &order, std::vector<uint8_t> &reversed, uint32_t (&units)[kBsShapes]);
 uint64_t bs_reverse_kmer(uint64_t kmer, int k);
 
 // exact_kernels.cu

@@ -41,12 +41,12 @@ __device__ __forceinline__ BsCarry bs_carry_init() {
 // reached in SOME column" and no separate accumulators are needed.  Because the levels are nested
 // (R0 <= R1 <= R2, also with the sticky bits), OR-ing in the old value of the same level subsumes
 // the insertion term (the old value of the level below): the sticky row costs the same five LOP3.
-template <int N, int FIRST, bool HIT>
+template <int N, int FIRST, bool HIT, int J0 = 0, int J1 = N>
 __device__ __forceinline__ void bs_rows(uint32_t (&r0)[N], uint32_t (&r1)[N], uint32_t (&r2)[N], BsCarry &c,
                                         const char *slot_lane, const uint32_t (&off)[N]) {
     const uint32_t ALL = 0xFFFFFFFFu;
 #pragma unroll
-    for (int j = 0; j < N; j++) {
+    for (int j = J0; j < J1; j++) { // rows J0..J1-1 of the N held in these arrays
         const int i = FIRST + j;
         const uint32_t e = *reinterpret_cast<const uint32_t *>(slot_lane + off[j]);
         const uint32_t o0 = r0[j], o1 = r1[j], o2 = r2[j];
@@ -66,6 +66,19 @@ __device__ __forceinline__ void bs_rows(uint32_t (&r0)[N], uint32_t (&r1)[N], ui
         c.n0p = n0; c.n1p = n1;
     }
 }
+
+// ---- dead-row skipping ------------------------------------------------------------------------------
+// Row i is non-zero in a column only where the k-mer's first i+1 bases match the text with <= 2 edits.  For
+// i >= 12 that is rare in unrelated sequence (about 4 % of the columns for the 1024 reads of a warp) — the
+// query k-mers are an adapter's windows, and the adapter sits in a few dozen columns of the sampled read
+// end.  So the rows are split at row M: rows < M (the TOP) are computed in every column; rows >= M (the
+// DEEP part: the end of the trunk and the tails, or the ends of the tails) only while something can reach
+// them.  Deep rows cannot change in a column when (a) level 2 of row M-1 is zero before and after the
+// column for every read of the warp (nested levels: then levels 0 and 1 are zero too) and (b) every deep
+// row except the sticky hit rows is zero: each term of their update is then zero, and a hit row only
+// keeps what it has.  (a) is one OR + one warp vote per column; (b) is re-established with an OR over the
+// deep rows + a vote only on the first quiet column after a busy stretch.
+constexpr int bs_check_row(int k) { return bs_check_row_host(k); } // apc_internal.h (the planner needs it too)
 
 template <int N, int FIRST>
 __device__ __forceinline__ void bs_rows_init(uint32_t (&r0)[N], uint32_t (&r1)[N], uint32_t (&r2)[N]) {
@@ -105,7 +118,7 @@ __device__ __forceinline__ uint32_t bs_next_job(unsigned int *job_counter, uint3
     s_mask[1][lane] = mb.x; s_mask[1][32 + lane] = mb.y; s_mask[1][64 + lane] = mb.z; s_mask[1][96 + lane] = mb.w;
 
 // One k-mer per warp.  kmers[u] is the k-mer of unit u, perm[u] its index in the caller's order.
-template <int K, int MB>
+template <int K, int MB, int M = bs_check_row(K)>
 __global__ void __launch_bounds__(32, MB)
 bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const uint32_t n_sg, const uint32_t cols,
                const uint32_t read_len, const uint64_t range_lo, const uint64_t range_hi,
@@ -130,16 +143,34 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
         for (uint32_t sg = jb * sg_per_job; sg < sg_end; sg++) {
             uint32_t r0[K], r1[K], r2[K];
             bs_rows_init<K, 0>(r0, r1, r2);
+            bool deep_zero = true; // rows M..K-2 are all zero (they start that way)
             const uint4 *p = planes + ((size_t)(sg_first + sg) * cols) * kGroupsPerSuper + lane;
             uint4 ma = __ldg(p), mb = __ldg(p + kGroupsPerSuper);
             for (uint32_t pr = 0; pr < pairs; pr++) {
                 p += 2 * kGroupsPerSuper;
                 const uint4 na = __ldg(p), nb = __ldg(p + kGroupsPerSuper); // buffer is padded by two columns
                 APC_BS_STAGE_MASKS()
-                BsCarry c = bs_carry_init();
-                bs_rows<K, 0, true>(r0, r1, r2, c, reinterpret_cast<const char *>(s_mask[0]) + lane * 4, off);
-                c = bs_carry_init();
-                bs_rows<K, 0, true>(r0, r1, r2, c, reinterpret_cast<const char *>(s_mask[1]) + lane * 4, off);
+#pragma unroll
+                for (int col = 0; col < 2; col++) {
+                    const char *slot = reinterpret_cast<const char *>(s_mask[col]) + lane * 4;
+                    BsCarry c = bs_carry_init();
+                    if constexpr (M >= K) {
+                        bs_rows<K, 0, true>(r0, r1, r2, c, slot, off);
+                    } else {
+                        const uint32_t before = r2[M - 1];
+                        bs_rows<K, 0, true, 0, M>(r0, r1, r2, c, slot, off);
+                        const bool alive = __any_sync(0xFFFFFFFFu, (before | r2[M - 1]) != 0);
+                        bool run = alive;
+                        if (!alive && !deep_zero) { // first quiet column: have the deep rows drained?
+                            uint32_t z = 0;
+#pragma unroll
+                            for (int j = M; j < K - 1; j++) z |= r2[j];
+                            run = __any_sync(0xFFFFFFFFu, z != 0);
+                        }
+                        deep_zero = !run;
+                        if (run) bs_rows<K, 0, true, M, K>(r0, r1, r2, c, slot, off);
+                    }
+                }
                 ma = na; mb = nb;
             }
             // hits of these 32 reads: [d<=0] + [d<=1] + [d<=2] (:589-593) = the sticky row k-1; reads outside
@@ -161,7 +192,7 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
 // share a suffix is stored reversed (bit 31 of its first perm entry) and walks the columns from
 // the last to the first: same code, negative column stride.
 // kmers[G*u .. G*u+G-1] are the k-mers of unit u, perm[] their indices in the caller's order.
-template <int K, int P, int G, int MB>
+template <int K, int P, int G, int MB, int M = bs_check_row(K)>
 __global__ void __launch_bounds__(32, MB)
 bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const uint32_t n_sg, const uint32_t cols,
                 const uint32_t read_len, const uint64_t range_lo, const uint64_t range_hi,
@@ -203,6 +234,7 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
             bs_rows_init<P, 0>(s0, s1, s2);
 #pragma unroll
             for (int g = 0; g < G; g++) bs_rows_init<T, P>(x0[g], x1[g], x2[g]);
+            bool deep_zero = true; // the deep rows other than the hit rows are all zero (they start that way)
             const uint4 *p = planes + ((size_t)(sg_first + sg) * cols + col0) * kGroupsPerSuper + lane;
             uint4 ma = __ldg(p), mb = __ldg(p + cstep);
             for (uint32_t pr = 0; pr < pairs; pr++) {
@@ -213,11 +245,64 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                 for (int col = 0; col < 2; col++) {
                     const char *slot = reinterpret_cast<const char *>(s_mask[col]) + lane * 4;
                     BsCarry c = bs_carry_init();
-                    bs_rows<P, 0, false>(s0, s1, s2, c, slot, off_s);
+                    if constexpr (M >= K) { // no deep part
+                        bs_rows<P, 0, false>(s0, s1, s2, c, slot, off_s);
 #pragma unroll
-                    for (int g = 0; g < G; g++) {
-                        BsCarry cg = c;
-                        bs_rows<T, P, true>(x0[g], x1[g], x2[g], cg, slot, off_t[g]);
+                        for (int g = 0; g < G; g++) {
+                            BsCarry cg = c;
+                            bs_rows<T, P, true>(x0[g], x1[g], x2[g], cg, slot, off_t[g]);
+                        }
+                    } else if constexpr (M <= P) { // top = trunk rows 0..M-1; deep = the rest of the trunk and the tails
+                        const uint32_t before = s2[M - 1];
+                        bs_rows<P, 0, false, 0, M>(s0, s1, s2, c, slot, off_s);
+                        const bool alive = __any_sync(0xFFFFFFFFu, (before | s2[M - 1]) != 0);
+                        bool run = alive;
+                        if (!alive && !deep_zero) { // first quiet column: have the deep rows drained?
+                            uint32_t z = 0;
+#pragma unroll
+                            for (int j = M; j < P; j++) z |= s2[j];
+#pragma unroll
+                            for (int g = 0; g < G; g++)
+#pragma unroll
+                                for (int j = 0; j < T - 1; j++) z |= x2[g][j];
+                            run = __any_sync(0xFFFFFFFFu, z != 0);
+                        }
+                        deep_zero = !run;
+                        if (run) {
+                            bs_rows<P, 0, false, M, P>(s0, s1, s2, c, slot, off_s);
+#pragma unroll
+                            for (int g = 0; g < G; g++) {
+                                BsCarry cg = c;
+                                bs_rows<T, P, true>(x0[g], x1[g], x2[g], cg, slot, off_t[g]);
+                            }
+                        }
+                    } else { // top = trunk + the first M-P rows of every tail; deep = the ends of the tails
+                        constexpr int S = M - P;
+                        bs_rows<P, 0, false>(s0, s1, s2, c, slot, off_s);
+                        BsCarry cg[G];
+                        uint32_t ck = 0;
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            cg[g] = c;
+                            ck |= x2[g][S - 1];
+                            bs_rows<T, P, true, 0, S>(x0[g], x1[g], x2[g], cg[g], slot, off_t[g]);
+                            ck |= x2[g][S - 1];
+                        }
+                        const bool alive = __any_sync(0xFFFFFFFFu, ck != 0);
+                        bool run = alive;
+                        if (!alive && !deep_zero) {
+                            uint32_t z = 0;
+#pragma unroll
+                            for (int g = 0; g < G; g++)
+#pragma unroll
+                                for (int j = S; j < T - 1; j++) z |= x2[g][j];
+                            run = __any_sync(0xFFFFFFFFu, z != 0);
+                        }
+                        deep_zero = !run;
+                        if (run) {
+#pragma unroll
+                            for (int g = 0; g < G; g++) bs_rows<T, P, true, S, T>(x0[g], x1[g], x2[g], cg[g], slot, off_t[g]);
+                        }
                     }
                 }
                 ma = na; mb = nb;

@@ -92,10 +92,15 @@ uint64_t bs_reverse_kmer(uint64_t kmer, int k) { // base order reversed (NOT com
 namespace {
 
 // Estimated cost of a unit in row-equivalents (one row = 5 LOP3 per column and 32 reads).  Measured
-// (tools/shape_bench.py, profiles/r01_shape_bench.jsonl): the time of a unit is proportional to its rows
-// whatever the shape (0.175 us per row and 1024 reads x 100 columns), plus about half a row for a grouped unit
-// (fewer resident warps than the one-k-mer kernel).
-inline float bs_unit_cost(int rows, int g) { return (float)rows + (g > 1 ? 0.5f : 0.f); }
+// (tools/shape_bench.py, profiles/r01_shape_bench.jsonl): the time of a unit is proportional to the rows it
+// computes whatever the shape, plus about half a row for a grouped unit (fewer resident warps than the
+// one-k-mer kernel).  With dead-row skipping (bitslice_core.cuh) a unit computes all its rows only in the
+// `alive` share of the columns and its top rows in the others.
+inline float bs_unit_cost(int k, int t, int g, float alive) {
+    const int p = k - t, rows = p + g * t, m = bs_check_row_host(k);
+    const int top = m >= k ? rows : m <= p ? m : p + g * (m - p);
+    return alive * (float)rows + (1.f - alive) * (float)top + (g > 1 ? 0.5f : 0.f);
+}
 
 struct BsGroup {
     uint32_t first; // position in the sorted array
@@ -107,18 +112,18 @@ struct BsShapeSet { // the shapes available for this k, most members first
     int id[kBsShapes], g[kBsShapes], shift[kBsShapes];
     float cost[kBsShapes];
     float single = 0.f;
-    BsShapeSet(int k, uint32_t shape_mask) {
+    BsShapeSet(int k, uint32_t shape_mask, float alive) {
         for (int s = 0; s < kBsShapes; s++) {
             const BsShape sh = (shape_mask >> s) & 1u ? bs_shape(k, s) : BsShape{0, 0};
             if (!sh.g) continue;
             id[n] = s;
             g[n] = sh.g;
             shift[n] = 2 * sh.t;
-            cost[n] = bs_unit_cost(k - sh.t + sh.g * sh.t, sh.g);
+            cost[n] = bs_unit_cost(k, sh.t, sh.g, alive);
             max_t = std::max(max_t, sh.t);
             n++;
         }
-        single = bs_unit_cost(k, 1);
+        single = bs_unit_cost(k, k, 1, alive); // one k-mer: no trunk, one tail of k rows
     }
 };
 
@@ -187,15 +192,16 @@ void bs_sort_keys(std::vector<BsKey> &a, std::vector<BsKey> &tmp, int k) {
 // a first cover of ALL k-mers in either direction tells which direction serves a k-mer better, then
 // each direction's k-mers are covered on their own (bs_cover).  order[] receives the k-mer indices in scan order
 // (units of shape 0, 1, ..., then singles), reversed[] whether the k-mer at that position is to be
-// stored reversed, units[s] the number of units of shape s.  shape_mask: the shapes that may be used.
-void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_mask, std::vector<uint32_t> &order,
-                      std::vector<uint8_t> &reversed, uint32_t (&units)[kBsShapes]) {
+// stored reversed, units[s] the number of units of shape s.  shape_mask: the shapes that may be used;
+// alive: the expected share of text columns in which a unit's deep rows are computed (bs_unit_cost).
+void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_mask, float alive,
+                      std::vector<uint32_t> &order, std::vector<uint8_t> &reversed, uint32_t (&units)[kBsShapes]) {
     order.resize(n);
     std::iota(order.begin(), order.end(), 0u);
     reversed.assign(n, 0);
     for (auto &u : units) u = 0;
     if (!shape_mask || k < 3 || n < 2) return;
-    const BsShapeSet ss(k, shape_mask);
+    const BsShapeSet ss(k, shape_mask, alive);
     if (ss.n == 0) return;
 
     std::vector<BsKey> sorted[2], tmp;

@@ -356,6 +356,8 @@ def run_b200(args, w):
         raise SystemExit("bench.py: the exact stage returned no query k-mers")
     counts = [torch.zeros(len(q), dtype=torch.int64, device=dev) for q in queries]
     for c, q in zip(ctxs, queries):
+        if args.plan_alive_pct >= 0:
+            c.set_option("plan_alive_pct", args.plan_alive_pct)
         c.set_queries(q, k)
 
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -610,6 +612,8 @@ def main():
     ap.add_argument("--lim", type=int, default=0, help="override the number of query k-mers (C5 sweep)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="weak: every rank holds its own n-read shard (default); strong: one n-read job split over the ranks")
+    ap.add_argument("--plan-alive-pct", type=int, default=-1,
+                    help="planner knob (apc_set_option plan_alive_pct): expected share of columns with live deep rows")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size, seconds of CPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

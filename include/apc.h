@@ -152,8 +152,9 @@ uint64_t apc_last_scan_launches(const apc_ctx *ctx);
  * of the persistent warps (0 auto): 32-read tiles for the row-packed
  * kernels, 1024-read super-groups for the bit-sliced one.  "shape_mask": the
  * unit shapes the default kernel may group k-mers into (bit s = shape s of
- * apc_plan_queries; default all, 0 = one k-mer per warp), applied at the next
- * apc_set_queries. */
+ * apc_plan_queries; default all, 0 = one k-mer per warp) and "plan_alive_pct":
+ * the share of text columns (percent) in which the planner expects a unit's
+ * deep rows to be computed; both applied at the next apc_set_queries. */
 int apc_set_option(apc_ctx *ctx, const char *name, int64_t value);
 
 /* The scan plan apc_set_queries would build for these k-mers (needs no GPU):
