@@ -500,8 +500,11 @@ def run_b200(args, w):
     # + the k-mers and the counts
     cols_padded = ((sl + 1 + 15) // 16) * 16
     hbm_bytes_launch = ((n + 1023) // 1024) * 32 * cols_padded * 16 + 16 * q_start
-    # What the ALU pipe really executes: the scan plan groups k-mers into units whose shared rows are
-    # computed once; every row of a unit costs 5 LOP3 per column and 32 reads (bitslice_core.cuh).
+    # What the scan plan costs on the ALU pipe: it groups k-mers into units whose shared rows are computed once;
+    # a row of a unit costs 5 LOP3 per column and 1024 reads (32 lanes x 32 reads; bitslice_core.cuh).  Dead-row
+    # skipping then leaves out the deep rows of a unit in the columns where nothing can reach them, which is
+    # data dependent: `planned` is the instruction count WITHOUT skipping (an upper bound of what is executed),
+    # the executed share is read from ncu (sm__inst_executed_pipe_alu, profiles/).
     from approx_counter_b200 import plan_queries
     plan_rows, plan_units, plan_reversed = [], [], []
     for q in queries:
@@ -512,8 +515,8 @@ def run_b200(args, w):
         plan_units.append([int(u) for u in pl["units"]])
         plan_reversed.append(int(pl["reversed"].sum()))
     n_sg_rank = (n + 1023) // 1024
-    lop3_lane_ops = sum(5.0 * rows * n_sg_rank * 1024 * (2 * ((L + 1) // 2)) for rows, L in zip(plan_rows, (sl, sl + 1)))
-    executed = lop3_lane_ops / (kern_ms / 1e3 / max(args.steps, 1))
+    lop3_lane_ops = sum(5.0 * 32 * rows * n_sg_rank * (2 * ((L + 1) // 2)) for rows, L in zip(plan_rows, (sl, sl + 1)))
+    planned = lop3_lane_ops / (kern_ms / 1e3 / max(args.steps, 1))
     roofline = {
         "bound": "int-alu", "kernel": "bs_group_kernel<K,P,G> (one launch per unit shape in use) + bs_scan_kernel<K> (ungrouped k-mers); "
                                       "one scan = up to 13 concurrent launches", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
@@ -522,11 +525,13 @@ def run_b200(args, w):
         "algorithmic_ops_per_column": ALGO_OPS_PER_COLUMN, "columns_per_launch": cols_launch,
         "avg_launch_ms": per_launch_s * 1e3, "scans_timed": n_scans, "launches_timed": n_launch,
         "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
-        "executed": {"lop3_Tlane_ops_per_s": executed / 1e12, "frac_of_alu_peak": executed / alu_peak,
-                     "rows_per_scan": plan_rows, "rows_if_one_kmer_per_warp": [len(q) * k for q in queries],
-                     "units_per_shape": plan_units, "kmers_scanned_backwards": plan_reversed,
-                     "note": "LOP3 the plan executes (5 per unit row, column and 32 reads) / time: the utilisation "
-                             "figure that cannot exceed 1; `frac` above is against the ALGORITHMIC 16 ops per column"},
+        "planned": {"lop3_Tlane_ops_per_s": planned / 1e12, "frac_of_alu_peak": planned / alu_peak,
+                    "rows_per_scan": plan_rows, "rows_if_one_kmer_per_warp": [len(q) * k for q in queries],
+                    "units_per_shape": plan_units, "kmers_scanned_backwards": plan_reversed,
+                    "note": "LOP3 of the scan plan if every unit row were computed in every column (5 per row, column "
+                            "and 1024 reads) / time, against the ALU peak; above 1 = what dead-row skipping saves. "
+                            "`frac` is against the ALGORITHMIC 16 ops per column; the executed utilisation is "
+                            "ncu_alu_pipe_pct"},
         "measured_int_peaks_Tops": {kk: v / 1e12 for kk, v in int_peak.items()},
         "frac_of_measured_lop3_peak": achieved / int_peak["lop3_ops_per_s"],
         "hbm": {"algorithmic_bytes_per_launch": hbm_bytes_launch,

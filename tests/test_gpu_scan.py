@@ -300,3 +300,50 @@ def test_units_of_every_shape_and_direction(counter, k):
         counter.set_option("scan_n_reads", -1)
     codes, offs = orc.encode(reads[lo:hi])
     assert np.array_equal(part, orc.error_count(codes, offs, kmers, k, fast=True))
+
+
+@pytest.mark.parametrize("k", [16, 17, 18, 20, 24, 27, 32])
+def test_deep_rows_wake_and_drain(counter, k):
+    """Dead-row skipping (rows >= 13/14 are computed only while level 2 of the row above is set for some read
+    of the warp, and until the deep rows have drained): reads made of adapter copies separated by gaps of every
+    length — partial copies, copies cut by the read end, back-to-back copies — wake and drain the deep rows over
+    and over; repetitive reads keep them awake all the time; a sample without any copy never wakes them."""
+    rng = np.random.default_rng(9100 + k)
+    motif = (ADAPTER * 2)[:max(k + 6, 28)]
+    kmers = []
+    for i in range(0, len(motif) - k + 1, 2):
+        w = motif[i:i + k]
+        kmers.append(orc.dna2int(w.decode()))
+        for _ in range(6):
+            kmers.append(orc.dna2int(mutate(rng, w, int(rng.integers(1, 3)))[:k].ljust(k, b"C").decode()))
+    kmers += [orc.dna2int("A" * k), orc.dna2int(("AC" * k)[:k]), orc.dna2int(("ACG" * k)[:k])]
+    kmers += [int.from_bytes(rng.bytes(8), "little") & ((1 << (2 * k)) - 1) for _ in range(8)]
+    kmers = np.array(kmers, np.uint64)
+
+    def gappy_read(L):
+        out = bytearray()
+        while len(out) < L:
+            out += rng.choice(ACGT, size=int(rng.integers(0, 45))).tobytes()
+            cut = int(rng.integers(k - 4, len(motif) + 1))
+            start = int(rng.integers(0, len(motif) - cut + 1))
+            out += mutate(rng, motif[start:start + cut], int(rng.integers(0, 4)))
+        return bytes(out[:L])
+
+    samples = {
+        "gappy": [gappy_read(int(rng.integers(150, 320))) for _ in range(1300)],
+        "repetitive": [(b"A" * 200), (b"AC" * 100), (b"ACG" * 70), motif * 6, b"N" * 50 + motif * 3] * 40
+                      + [gappy_read(200) for _ in range(100)],
+        "quiet": [rng.choice(ACGT, size=int(rng.integers(60, 160))).tobytes() for _ in range(1100)],
+    }
+    for name, reads in samples.items():
+        counter.set_option("scan_variant", 0)
+        counter.upload_sample(reads)
+        got = counter.errorCount(kmers, k)
+        codes, offs = orc.encode(reads)
+        want = orc.error_count(codes, offs, kmers, k, fast=True)
+        assert np.array_equal(got, want), name
+        counter.set_option("shape_mask", 0)            # one k-mer per warp: the same split of the rows, no units
+        try:
+            assert np.array_equal(counter.errorCount(kmers, k), want), name
+        finally:
+            counter.set_option("shape_mask", 0xFFFFFFFF)

@@ -10,9 +10,9 @@ for w in ${WORKLOADS:-C1 C3 C4}; do
   echo "bench $w rc=$? $(cut -c1-140 gpurun_out/bench_$w.json)"
 done
 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > /dev/null 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_c2_v7.csv \
-  python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_v7.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_c2_v8.csv \
+  python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_v8.log 2>&1
 echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:bs_group -s 36 -c 1 -o gpurun_out/bs_c2_v7 -f \
-  python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_v7.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:bs_group_kernel<16, 8, 4' -s 4 -c 1 -o gpurun_out/bs_c2_v8 -f \
+  python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_v8.log 2>&1
 echo "ncu full rc=$?"
