@@ -358,6 +358,8 @@ def run_b200(args, w):
     for c, q in zip(ctxs, queries):
         if args.plan_alive_pct >= 0:
             c.set_option("plan_alive_pct", args.plan_alive_pct)
+        if args.sg_per_job > 0:
+            c.set_option("tiles_per_job", args.sg_per_job)
         c.set_queries(q, k)
 
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
@@ -619,6 +621,8 @@ def main():
                     help="weak: every rank holds its own n-read shard (default); strong: one n-read job split over the ranks")
     ap.add_argument("--plan-alive-pct", type=int, default=-1,
                     help="planner knob (apc_set_option plan_alive_pct): expected share of columns with live deep rows")
+    ap.add_argument("--sg-per-job", type=int, default=0,
+                    help="tuning knob (apc_set_option tiles_per_job): 1024-read super-groups per job, 0 = auto")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size, seconds of CPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
