@@ -5,7 +5,7 @@ mkdir -p gpurun_out; : > gpurun_out/sweep_c5.jsonl
 if [ "$1" = full ]; then
   points="10000:500 10000:5000 10000:50000 100000:500 100000:5000 100000:50000 1000000:500 1000000:5000 1000000:50000 10000000:500 10000000:5000 10000000:50000"
 else
-  points="10000:500 100000:5000 1000000:5000 1000000:50000 10000000:500 10000000:5000"
+  points=${SWEEP_POINTS:-"10000:500 100000:5000 1000000:5000 1000000:50000 10000000:500 10000000:5000"}
 fi
 for pt in $points; do
   n=${pt%%:*}; q=${pt##*:}
