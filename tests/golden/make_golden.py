@@ -3,7 +3,8 @@
 The reference ships no tests or golden vectors and cannot be built here (SeqAn is
 absent), so these fixtures are produced by the CPU restatement in oracle/ and
 cross-checked, where small enough, against the literal SeqAn search-scheme model
-(oracle/seqan_model.cpp).  PARITY UNPINNED — they pin the GPU path and the oracle
+(oracle/seqan_model.cpp) and, all of them, against the same recursion over an own
+bidirectional FM index (oracle/fm_index_model.cpp).  PARITY UNPINNED — they pin the GPU path and the oracle
 against regressions, not against a SeqAn build.  Run from the repo root:
 
     python tests/golden/make_golden.py
@@ -59,8 +60,12 @@ def approx_case(seed, n, L, k, n_kmers, with_model):
     if with_model:
         model = orc.seqan_model_error_count(codes, offs, kmers, k)
         assert np.array_equal(model, slow), (model, slow)
+    # the same recursion over a real bidirectional FM index (oracle/fm_index_model.cpp): every case, any size
+    fm = orc.fm_index_error_count(codes, offs, kmers, k)
+    assert np.array_equal(fm, slow), (fm, slow)
     return {"k": k, "reads": reads, "kmers": [orc.int2dna(v, k) for v in kmers],
-            "counts": [int(c) for c in slow], "checked_against_seqan_model": bool(with_model)}
+            "counts": [int(c) for c in slow], "checked_against_seqan_model": bool(with_model),
+            "checked_against_fm_index_model": True}
 
 
 def exact_case(seed, n, L, k, param_lc, lim):

@@ -50,6 +50,7 @@ def test_golden_approx(case):
     assert orc.error_count(codes, offs, kmers, k, fast=True).tolist() == case["counts"]
     if len(case["reads"]) <= 30:
         assert orc.error_count(codes, offs, kmers, k).tolist() == case["counts"]
+    assert orc.fm_index_error_count(codes, offs, kmers, k).tolist() == case["counts"]   # the index-based form
 
 
 @pytest.mark.parametrize("variant", [0, 1])
