@@ -150,25 +150,33 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
                 p += 2 * kGroupsPerSuper;
                 const uint4 na = __ldg(p), nb = __ldg(p + kGroupsPerSuper); // buffer is padded by two columns
                 APC_BS_STAGE_MASKS()
-#pragma unroll
-                for (int col = 0; col < 2; col++) {
-                    const char *slot = reinterpret_cast<const char *>(s_mask[col]) + lane * 4;
+                const char *slot_a = reinterpret_cast<const char *>(s_mask[0]) + lane * 4;
+                const char *slot_b = reinterpret_cast<const char *>(s_mask[1]) + lane * 4;
+                if constexpr (M >= K) {
                     BsCarry c = bs_carry_init();
-                    if constexpr (M >= K) {
-                        bs_rows<K, 0, true>(r0, r1, r2, c, slot, off);
-                    } else {
-                        const uint32_t before = r2[M - 1];
-                        bs_rows<K, 0, true, 0, M>(r0, r1, r2, c, slot, off);
-                        const bool alive = __any_sync(0xFFFFFFFFu, (before | r2[M - 1]) != 0);
-                        bool run = alive;
-                        if (!alive && !deep_zero) { // first quiet column: have the deep rows drained?
-                            uint32_t z = 0;
+                    bs_rows<K, 0, true>(r0, r1, r2, c, slot_a, off);
+                    c = bs_carry_init();
+                    bs_rows<K, 0, true>(r0, r1, r2, c, slot_b, off);
+                } else {
+                    // top rows of both columns first (they do not depend on the deep rows), one test per column pair
+                    uint32_t ck = r2[M - 1];
+                    BsCarry ca = bs_carry_init();
+                    bs_rows<K, 0, true, 0, M>(r0, r1, r2, ca, slot_a, off);
+                    ck |= r2[M - 1];
+                    BsCarry cb = bs_carry_init();
+                    bs_rows<K, 0, true, 0, M>(r0, r1, r2, cb, slot_b, off);
+                    ck |= r2[M - 1];
+                    bool run = __any_sync(0xFFFFFFFFu, ck != 0);
+                    if (!run && !deep_zero) { // first quiet pair: have the deep rows drained?
+                        uint32_t z = 0;
 #pragma unroll
-                            for (int j = M; j < K - 1; j++) z |= r2[j];
-                            run = __any_sync(0xFFFFFFFFu, z != 0);
-                        }
-                        deep_zero = !run;
-                        if (run) bs_rows<K, 0, true, M, K>(r0, r1, r2, c, slot, off);
+                        for (int j = M; j < K - 1; j++) z |= r2[j];
+                        run = __any_sync(0xFFFFFFFFu, z != 0);
+                    }
+                    deep_zero = !run;
+                    if (run) {
+                        bs_rows<K, 0, true, M, K>(r0, r1, r2, ca, slot_a, off);
+                        bs_rows<K, 0, true, M, K>(r0, r1, r2, cb, slot_b, off);
                     }
                 }
                 ma = na; mb = nb;
@@ -241,6 +249,45 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                 p += 2 * cstep;
                 const uint4 na = __ldg(p), nb = __ldg(p + cstep); // the buffer is padded by two columns at both ends
                 APC_BS_STAGE_MASKS()
+                if constexpr (M < K && M <= P) {
+                    // top = trunk rows 0..M-1; deep = the rest of the trunk and the tails.  The top rows of both
+                    // columns first (they do not depend on the deep rows), then one test per column pair.
+                    const char *slot_a = reinterpret_cast<const char *>(s_mask[0]) + lane * 4;
+                    const char *slot_b = reinterpret_cast<const char *>(s_mask[1]) + lane * 4;
+                    uint32_t ck = s2[M - 1];
+                    BsCarry ca = bs_carry_init();
+                    bs_rows<P, 0, false, 0, M>(s0, s1, s2, ca, slot_a, off_s);
+                    ck |= s2[M - 1];
+                    BsCarry cb = bs_carry_init();
+                    bs_rows<P, 0, false, 0, M>(s0, s1, s2, cb, slot_b, off_s);
+                    ck |= s2[M - 1];
+                    bool run = __any_sync(0xFFFFFFFFu, ck != 0);
+                    if (!run && !deep_zero) { // first quiet pair: have the deep rows drained?
+                        uint32_t z = 0;
+#pragma unroll
+                        for (int j = M; j < P; j++) z |= s2[j];
+#pragma unroll
+                        for (int g = 0; g < G; g++)
+#pragma unroll
+                            for (int j = 0; j < T - 1; j++) z |= x2[g][j];
+                        run = __any_sync(0xFFFFFFFFu, z != 0);
+                    }
+                    deep_zero = !run;
+                    if (run) {
+                        bs_rows<P, 0, false, M, P>(s0, s1, s2, ca, slot_a, off_s);
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            BsCarry cg = ca;
+                            bs_rows<T, P, true>(x0[g], x1[g], x2[g], cg, slot_a, off_t[g]);
+                        }
+                        bs_rows<P, 0, false, M, P>(s0, s1, s2, cb, slot_b, off_s);
+#pragma unroll
+                        for (int g = 0; g < G; g++) {
+                            BsCarry cg = cb;
+                            bs_rows<T, P, true>(x0[g], x1[g], x2[g], cg, slot_b, off_t[g]);
+                        }
+                    }
+                } else
 #pragma unroll
                 for (int col = 0; col < 2; col++) {
                     const char *slot = reinterpret_cast<const char *>(s_mask[col]) + lane * 4;
@@ -252,30 +299,7 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                             BsCarry cg = c;
                             bs_rows<T, P, true>(x0[g], x1[g], x2[g], cg, slot, off_t[g]);
                         }
-                    } else if constexpr (M <= P) { // top = trunk rows 0..M-1; deep = the rest of the trunk and the tails
-                        const uint32_t before = s2[M - 1];
-                        bs_rows<P, 0, false, 0, M>(s0, s1, s2, c, slot, off_s);
-                        const bool alive = __any_sync(0xFFFFFFFFu, (before | s2[M - 1]) != 0);
-                        bool run = alive;
-                        if (!alive && !deep_zero) { // first quiet column: have the deep rows drained?
-                            uint32_t z = 0;
-#pragma unroll
-                            for (int j = M; j < P; j++) z |= s2[j];
-#pragma unroll
-                            for (int g = 0; g < G; g++)
-#pragma unroll
-                                for (int j = 0; j < T - 1; j++) z |= x2[g][j];
-                            run = __any_sync(0xFFFFFFFFu, z != 0);
-                        }
-                        deep_zero = !run;
-                        if (run) {
-                            bs_rows<P, 0, false, M, P>(s0, s1, s2, c, slot, off_s);
-#pragma unroll
-                            for (int g = 0; g < G; g++) {
-                                BsCarry cg = c;
-                                bs_rows<T, P, true>(x0[g], x1[g], x2[g], cg, slot, off_t[g]);
-                            }
-                        }
+                    } else if constexpr (M <= P) { // handled per column PAIR above the column loop
                     } else { // top = trunk + the first M-P rows of every tail; deep = the ends of the tails
                         constexpr int S = M - P;
                         bs_rows<P, 0, false>(s0, s1, s2, c, slot, off_s);
