@@ -113,6 +113,21 @@ __device__ __forceinline__ uint32_t bs_next_job(unsigned int *job_counter, uint3
     return __shfl_sync(0xFFFFFFFFu, job, 0);
 }
 
+// A/B builds with -DAPC_BS_STATS count, per column pair (or column), how often the deep rows were computed:
+// apc_microbench("bs_stats") returns computed / total and resets the counters (tools/build_ab.sh).
+#ifdef APC_BS_STATS
+static __device__ unsigned long long g_bs_stats[2];
+#define APC_BS_STAT(run_)                                                             \
+    do {                                                                              \
+        if (lane == 0) {                                                              \
+            atomicAdd(&g_bs_stats[1], 1ull);                                          \
+            if (run_) atomicAdd(&g_bs_stats[0], 1ull);                                \
+        }                                                                             \
+    } while (0)
+#else
+#define APC_BS_STAT(run_) do { } while (0)
+#endif
+
 #define APC_BS_STAGE_MASKS()                                                                                          \
     s_mask[0][lane] = ma.x; s_mask[0][32 + lane] = ma.y; s_mask[0][64 + lane] = ma.z; s_mask[0][96 + lane] = ma.w;   \
     s_mask[1][lane] = mb.x; s_mask[1][32 + lane] = mb.y; s_mask[1][64 + lane] = mb.z; s_mask[1][96 + lane] = mb.w;
@@ -174,6 +189,7 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
                         run = __any_sync(0xFFFFFFFFu, z != 0);
                     }
                     deep_zero = !run;
+                    APC_BS_STAT(run);
                     if (run) {
                         bs_rows<K, 0, true, M, K>(r0, r1, r2, ca, slot_a, off);
                         bs_rows<K, 0, true, M, K>(r0, r1, r2, cb, slot_b, off);
@@ -273,6 +289,7 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                         run = __any_sync(0xFFFFFFFFu, z != 0);
                     }
                     deep_zero = !run;
+                    APC_BS_STAT(run);
                     if (run) {
                         bs_rows<P, 0, false, M, P>(s0, s1, s2, ca, slot_a, off_s);
 #pragma unroll
@@ -323,6 +340,8 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                             run = __any_sync(0xFFFFFFFFu, z != 0);
                         }
                         deep_zero = !run;
+                        APC_BS_STAT(run);
+                    APC_BS_STAT(run);
                         if (run) {
 #pragma unroll
                             for (int g = 0; g < G; g++) bs_rows<T, P, true, S, T>(x0[g], x1[g], x2[g], cg[g], slot, off_t[g]);

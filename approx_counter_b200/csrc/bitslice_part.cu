@@ -31,4 +31,15 @@ cudaError_t APC_BS_CAT(launch_bs_part, APC_BS_PART)(BsLaunchCtx &l) {
     }
 }
 
+#ifdef APC_BS_STATS
+// deep rows computed / tests, of the kernels of this object since the last call; resets the counters
+cudaError_t APC_BS_CAT(bs_stats_part, APC_BS_PART)(double *ratio) {
+    unsigned long long h[2] = {0, 0}, z[2] = {0, 0};
+    cudaError_t e = cudaMemcpyFromSymbol(h, g_bs_stats, sizeof(h));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_bs_stats, z, sizeof(z));
+    *ratio = h[1] ? (double)h[0] / (double)h[1] : -1.0;
+    return e;
+}
+#endif
+
 } // namespace apc

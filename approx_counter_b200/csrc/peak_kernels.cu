@@ -179,7 +179,26 @@ static cudaError_t time_scan_core(const Ctx &c, uint32_t *d_out, double *unit_co
     return cudaGetLastError();
 }
 
+#ifdef APC_BS_STATS
+cudaError_t bs_stats_part0(double *);
+cudaError_t bs_stats_part1(double *);
+cudaError_t bs_stats_part2(double *);
+cudaError_t bs_stats_part3(double *);
+#endif
+
 cudaError_t microbench(const Ctx &c, const char *name, double *value) {
+#ifdef APC_BS_STATS
+    if (!std::strcmp(name, "bs_stats")) {
+        cudaError_t e = cudaStreamSynchronize(c.stream);
+        if (e != cudaSuccess) return e;
+        switch (c.k & 3) {
+        case 0: return bs_stats_part0(value);
+        case 1: return bs_stats_part1(value);
+        case 2: return bs_stats_part2(value);
+        default: return bs_stats_part3(value);
+        }
+    }
+#endif
     uint32_t *d_out = nullptr;
     cudaError_t e = cudaMalloc((void **)&d_out, 16);
     if (e != cudaSuccess) return e;

@@ -408,6 +408,9 @@ def run_b200(args, w):
     barrier()
     t_mark1 = time.perf_counter()
     clocks = sampler.stop(t_mark0, t_mark1) if sampler is not None else None
+    if os.environ.get("APC_BS_STATS"):  # A/B library built with -DAPC_BS_STATS (tools/build_ab.sh)
+        log("[bs_stats] share of tests after which the deep rows were computed:",
+            [round(c.microbench("bs_stats"), 4) for c in ctxs])
     dev_ms = sum(a.elapsed_time(b) for a, b in step_events)
     kern_ms = sum(a.elapsed_time(b) for a, b in kernel_events)
     n_launch = launches[0]

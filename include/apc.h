@@ -183,7 +183,9 @@ int apc_measure_int_peak(apc_ctx *ctx, double *lop3_ops_per_s,
  * "lop3", "imad", "mixed", "imad_hi", "imad_wide" return lane-ops
  * per second; "core_<sets>_<threads>_<ctas>" (see peak_kernels.cu) run
  * the scan kernel's column update from registers (no loads) and return
- * unit-columns per second. */
+ * unit-columns per second.  "bs_stats" exists only in counting builds
+ * (-DAPC_BS_STATS): share of the dead-row tests after which the deep rows
+ * were computed since the last call. */
 int apc_microbench(apc_ctx *ctx, const char *name, double *value);
 
 #ifdef __cplusplus
