@@ -304,7 +304,7 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                             bs_rows<T, P, true>(x0[g], x1[g], x2[g], cg, slot_b, off_t[g]);
                         }
                     }
-                } else
+                } else {
 #pragma unroll
                 for (int col = 0; col < 2; col++) {
                     const char *slot = reinterpret_cast<const char *>(s_mask[col]) + lane * 4;
@@ -316,8 +316,7 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                             BsCarry cg = c;
                             bs_rows<T, P, true>(x0[g], x1[g], x2[g], cg, slot, off_t[g]);
                         }
-                    } else if constexpr (M <= P) { // handled per column PAIR above the column loop
-                    } else { // top = trunk + the first M-P rows of every tail; deep = the ends of the tails
+                    } else { // M > P: top = trunk + the first M-P rows of every tail; deep = the ends of the tails (per column)
                         constexpr int S = M - P;
                         bs_rows<P, 0, false>(s0, s1, s2, c, slot, off_s);
                         BsCarry cg[G];
@@ -341,12 +340,12 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                         }
                         deep_zero = !run;
                         APC_BS_STAT(run);
-                    APC_BS_STAT(run);
                         if (run) {
 #pragma unroll
                             for (int g = 0; g < G; g++) bs_rows<T, P, true, S, T>(x0[g], x1[g], x2[g], cg[g], slot, off_t[g]);
                         }
                     }
+                }
                 }
                 ma = na; mb = nb;
             }
