@@ -260,3 +260,46 @@ def test_fm_index_model_ragged_and_degenerate():
     assert orc.fm_index_error_count(codes, offs, [5, 6], 8).tolist() == [0, 0]
     with pytest.raises(ValueError):
         orc.fm_index_error_count(codes, offs, [1], 3)      # the four blocks of the scheme need k >= 4
+
+
+def _end_distances(pattern, text):
+    """d[j] = min edit distance of `pattern` to a substring of `text` ENDING at position j (j = 0..len(text))."""
+    m = len(pattern)
+    col = list(range(m + 1))
+    out = [col[m]]
+    for ch in text:
+        new = [0] * (m + 1)
+        for i in range(1, m + 1):
+            new[i] = min(col[i - 1] + (pattern[i - 1] != ch or ch == "N"), col[i] + 1, new[i - 1] + 1)
+        col = new
+        out.append(col[m])
+    return out
+
+
+def test_split_identity():
+    """The identity a two-sided (meet-in-the-middle) scan would rest on: for a k-mer
+    AB, min over substrings of d(AB, substring) = min over text positions j of
+    [min d(A, substring ending at j)] + [min d(B, substring starting at j)] — the same reversal argument that lets
+    suffix-sharing units walk the text backwards.  Checked against the oracle's minimum infix distance."""
+    rng = np.random.default_rng(4242)
+    for trial in range(60):
+        k = int(rng.integers(6, 25))
+        L = int(rng.integers(k - 3, 70))
+        text = "".join(rng.choice(list("ACGTN"), size=L, p=[0.24, 0.24, 0.24, 0.24, 0.04]))
+        kmer = "".join(rng.choice(list("ACGT"), size=k))
+        if trial % 2:   # plant a noisy copy so that small distances occur
+            m = list(kmer)
+            for _ in range(int(rng.integers(0, 4))):
+                p = int(rng.integers(0, len(m)))
+                m[p] = str(rng.choice(list("ACGT")))
+            m = "".join(m)[: max(0, L)]
+            pos = int(rng.integers(0, max(1, L - len(m) + 1)))
+            text = (text[:pos] + m + text[pos + len(m):])[:L]
+        for cut in (k // 2, k // 3, k - 2):
+            a, b = kmer[:cut], kmer[cut:]
+            fwd = _end_distances(a, text)                              # A ending at j
+            bwd = _end_distances(b[::-1], text[::-1])[::-1]            # B starting at j
+            split = min(x + y for x, y in zip(fwd, bwd))
+            codes, _ = orc.encode([text])
+            want = orc.min_infix_distance(codes, orc.dna2int(kmer), k)  # clamped at 3
+            assert min(split, 3) == want, (kmer, text, cut, split, want)
