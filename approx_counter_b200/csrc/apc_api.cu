@@ -71,7 +71,7 @@ static int prepare_sample(Ctx *c, uint64_t n_reads, uint32_t max_len, uint64_t t
     // either end for the kernels' prefetch (forward and backward walks)
     const size_t n_sg = ((size_t)c->n_tiles + 31) / 32;
     c->planes_bytes = n_sg * c->chunks * kChunkBases * 32 * sizeof(uint4);
-    if ((st = grow(c, c->d_planes, c->planes_cap, c->planes_bytes + 4 * 32 * sizeof(uint4)))) return st;
+    if ((st = grow(c, c->d_planes, c->planes_cap, c->planes_bytes + 2 * apc::kBsPadCols * 32 * sizeof(uint4)))) return st;
     const size_t lens_bytes = ((size_t)c->n_tiles * kTileReads + 1) * sizeof(uint32_t);
     if ((st = grow(c, c->d_lens, c->lens_cap, lens_bytes))) return st;
     APC_CUDA(c, cudaMemsetAsync(c->d_lens, 0, lens_bytes, c->stream));

@@ -59,6 +59,12 @@ constexpr int bs_check_row_host(int k) {
     return k >= 18 ? 14 : k >= 16 ? 13 : k;
 #endif
 }
+// Column pairs of the bit planes a scan kernel keeps in flight ahead of the pair it computes (A/B builds:
+// -DAPC_BS_PREFETCH_PAIRS=2 or 3); the plane buffer is padded by that many columns at either end.
+#ifndef APC_BS_PREFETCH_PAIRS
+#define APC_BS_PREFETCH_PAIRS 1
+#endif
+constexpr int kBsPadCols = 2 * APC_BS_PREFETCH_PAIRS;
 struct BsRange { // super-groups (1024 reads) and reads [lo, hi) of one scan
     uint32_t sg_first, n_sg;
     uint64_t lo, hi;
@@ -105,9 +111,9 @@ struct Ctx {
     uint4 *d_tiles = nullptr;
     size_t tiles_bytes = 0;
     uint4 *d_planes = nullptr;  // bit planes of the same text (bitslice_kernel.cu), [super-group][column][32 groups],
-                                // two columns of padding in front and behind (the kernels prefetch past both ends)
+                                // kBsPadCols columns of padding in front and behind (the kernels prefetch past both ends)
     size_t planes_cap = 0, planes_bytes = 0;
-    uint4 *planes() const { return d_planes + 2 * 32; }
+    uint4 *planes() const { return d_planes + kBsPadCols * 32; }
     uint32_t *d_lens = nullptr; // per-read length — exact stage
     size_t lens_cap = 0;
     bool has_sample = false;

@@ -128,6 +128,28 @@ static __device__ unsigned long long g_bs_stats[2];
 #define APC_BS_STAT(run_) do { } while (0)
 #endif
 
+// Plane prefetch: the column pair after the one being computed is always in registers (na, nb); deeper
+// builds (APC_BS_PREFETCH_PAIRS = D > 1) keep D - 1 more pairs in flight in qa[], qb[].
+#if APC_BS_PREFETCH_PAIRS == 1
+#define APC_BS_PREFETCH_INIT(p_, step_)
+#define APC_BS_PREFETCH_NEXT(p_, step_) const uint4 na = __ldg(p_), nb = __ldg((p_) + (step_));
+#else
+#define APC_BS_PREFETCH_INIT(p_, step_)                                                          \
+    uint4 qa[APC_BS_PREFETCH_PAIRS], qb[APC_BS_PREFETCH_PAIRS];                                  \
+    _Pragma("unroll") for (int d_ = 0; d_ < APC_BS_PREFETCH_PAIRS; d_++) {                       \
+        qa[d_] = __ldg((p_) + (2 * (d_ + 1)) * (step_));                                         \
+        qb[d_] = __ldg((p_) + (2 * (d_ + 1) + 1) * (step_));                                     \
+    }
+#define APC_BS_PREFETCH_NEXT(p_, step_)                                                          \
+    const uint4 na = qa[0], nb = qb[0];                                                          \
+    _Pragma("unroll") for (int d_ = 0; d_ + 1 < APC_BS_PREFETCH_PAIRS; d_++) {                   \
+        qa[d_] = qa[d_ + 1];                                                                     \
+        qb[d_] = qb[d_ + 1];                                                                     \
+    }                                                                                            \
+    qa[APC_BS_PREFETCH_PAIRS - 1] = __ldg((p_) + (2 * APC_BS_PREFETCH_PAIRS) * (step_));         \
+    qb[APC_BS_PREFETCH_PAIRS - 1] = __ldg((p_) + (2 * APC_BS_PREFETCH_PAIRS + 1) * (step_));
+#endif
+
 #define APC_BS_STAGE_MASKS()                                                                                          \
     s_mask[0][lane] = ma.x; s_mask[0][32 + lane] = ma.y; s_mask[0][64 + lane] = ma.z; s_mask[0][96 + lane] = ma.w;   \
     s_mask[1][lane] = mb.x; s_mask[1][32 + lane] = mb.y; s_mask[1][64 + lane] = mb.z; s_mask[1][96 + lane] = mb.w;
@@ -161,9 +183,10 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
             bool deep_zero = true; // rows M..K-2 are all zero (they start that way)
             const uint4 *p = planes + ((size_t)(sg_first + sg) * cols) * kGroupsPerSuper + lane;
             uint4 ma = __ldg(p), mb = __ldg(p + kGroupsPerSuper);
+            APC_BS_PREFETCH_INIT(p, kGroupsPerSuper)
             for (uint32_t pr = 0; pr < pairs; pr++) {
                 p += 2 * kGroupsPerSuper;
-                const uint4 na = __ldg(p), nb = __ldg(p + kGroupsPerSuper); // buffer is padded by two columns
+                APC_BS_PREFETCH_NEXT(p, kGroupsPerSuper) // defines na, nb; the buffer is padded by kBsPadCols columns
                 APC_BS_STAGE_MASKS()
                 const char *slot_a = reinterpret_cast<const char *>(s_mask[0]) + lane * 4;
                 const char *slot_b = reinterpret_cast<const char *>(s_mask[1]) + lane * 4;
@@ -261,9 +284,10 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
             bool deep_zero = true; // the deep rows other than the hit rows are all zero (they start that way)
             const uint4 *p = planes + ((size_t)(sg_first + sg) * cols + col0) * kGroupsPerSuper + lane;
             uint4 ma = __ldg(p), mb = __ldg(p + cstep);
+            APC_BS_PREFETCH_INIT(p, cstep)
             for (uint32_t pr = 0; pr < pairs; pr++) {
                 p += 2 * cstep;
-                const uint4 na = __ldg(p), nb = __ldg(p + cstep); // the buffer is padded by two columns at both ends
+                APC_BS_PREFETCH_NEXT(p, cstep) // defines na, nb; the buffer is padded by kBsPadCols columns at both ends
                 APC_BS_STAGE_MASKS()
                 if constexpr (M < K && M <= P) {
                     // top = trunk rows 0..M-1; deep = the rest of the trunk and the tails.  The top rows of both

@@ -72,7 +72,7 @@ build_planes_kernel(const uint4 *__restrict__ tiles, const uint32_t n_tiles, con
 cudaError_t launch_build_planes(const Ctx &c) {
     if (c.n_tiles == 0 || c.chunks == 0) return cudaSuccess;
     // groups past the last tile match nothing; the padding columns in front and behind are loaded but never used
-    cudaError_t e = cudaMemsetAsync(c.d_planes, 0, c.planes_bytes + 4 * kGroupsPerSuper * sizeof(uint4), c.stream);
+    cudaError_t e = cudaMemsetAsync(c.d_planes, 0, c.planes_bytes + 2 * kBsPadCols * kGroupsPerSuper * sizeof(uint4), c.stream);
     if (e != cudaSuccess) return e;
     const unsigned blocks = (c.n_tiles + 7) / 8;
     build_planes_kernel<<<blocks, 256, 0, c.stream>>>(c.d_tiles, c.n_tiles, c.chunks, c.planes());
