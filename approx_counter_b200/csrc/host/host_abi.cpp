@@ -87,6 +87,7 @@ int apch_reads_load(const char *path, apch_reads **out) {
 uint64_t apch_reads_count(const apch_reads *r) { return r ? r->size() : 0; }
 uint64_t apch_reads_length(const apch_reads *r, uint64_t i) { return r->length(i); }
 const char *apch_reads_seq(const apch_reads *r, uint64_t i) { return r->seq(i); }
+int apch_reads_mapped(const apch_reads *r) { return r && r->mapping ? 1 : 0; }
 void apch_reads_free(apch_reads *r) { delete r; }
 
 int apch_sample(const apch_reads *r, uint64_t nb_sample, uint64_t cut, int bot, int64_t seed, uint8_t *out,

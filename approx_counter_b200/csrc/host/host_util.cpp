@@ -11,6 +11,10 @@
 #include <random>
 #ifdef _OPENMP
 #include <omp.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #endif
 
 namespace apch {
@@ -276,9 +280,129 @@ const char *next_record(const char *begin, const char *p, const char *end, bool 
     return end;
 }
 
+// ---- zero-copy path: records whose sequence sits on ONE line, parsed straight from a read-only mapping ----
+struct MapPiece {
+    const char *begin = nullptr, *end = nullptr;
+    std::vector<uint64_t> starts, lens; // file offsets and lengths of the sequences
+    bool ok = true;      // false: malformed (the copying parser will report it)
+    bool simple = true;  // false: a multi-line record or blanks inside a sequence line -> use the copying parser
+};
+
+void parse_piece_mapped(MapPiece &pc, const char *file_begin, bool fastq) {
+    const char *p = pc.begin, *end = pc.end;
+    const char stop = fastq ? '+' : '>';
+    while (true) {
+        p = skip_blank(p, end);
+        if (p >= end) break;
+        if (*p != (fastq ? '@' : '>')) { pc.ok = false; return; }
+        p = line_end(p, end); // header line
+        if (p < end) p++;
+        const char *s = p, *e = p;
+        if (p < end && *p != stop) { // the sequence line
+            e = line_end(p, end);
+            p = e < end ? e + 1 : end;
+            while (e > s && (e[-1] == '\r' || e[-1] == ' ' || e[-1] == '\t')) e--;
+            if (memchr(s, ' ', (size_t)(e - s)) || memchr(s, '\t', (size_t)(e - s)) || memchr(s, '\r', (size_t)(e - s))) {
+                pc.simple = false;
+                return;
+            }
+            // anything but the stop character (or, FASTA, the end / blank lines) next means a second sequence line
+            const char *q = fastq ? p : skip_blank(p, end);
+            if (q < end && *q != stop) { pc.simple = false; return; }
+            if (fastq && q >= end) { pc.ok = false; return; }
+        } else if (fastq && p >= end) {
+            pc.ok = false;
+            return;
+        }
+        const uint64_t n = (uint64_t)(e - s);
+        if (fastq) {
+            p = line_end(p, end); // '+' line
+            if (p < end) p++;
+            uint64_t q = 0; // the quality string may contain '@' and '>': count characters
+            while (p < end && q < n) {
+                const char *le = line_end(p, end);
+                const char *t = le;
+                while (t > p && t[-1] == '\r') t--;
+                q += (uint64_t)(t - p);
+                p = le < end ? le + 1 : end;
+            }
+        }
+        pc.starts.push_back((uint64_t)(s - file_begin));
+        pc.lens.push_back(n);
+    }
+}
+
+// Returns true when `out` was filled from a mapping of the file; false = use the copying parser (small file, pipe,
+// multi-line records, anything unusual or malformed).
+bool read_fastx_mapped(const std::string &path, Reads &out) {
+    size_t min_bytes = (size_t)1 << 25;
+    if (const char *env = getenv("APCH_MMAP_BYTES")) min_bytes = strtoull(env, nullptr, 10); // tests; 0 disables
+    if (min_bytes == 0) return false;
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || (size_t)st.st_size < min_bytes) {
+        close(fd);
+        return false;
+    }
+    const size_t size = (size_t)st.st_size;
+    void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return false;
+    madvise(m, size, MADV_SEQUENTIAL);
+    std::shared_ptr<const char> mapping((const char *)m, [size](const char *q) { munmap((void *)q, size); });
+    const char *begin = mapping.get(), *end = begin + size;
+    const char *p0 = skip_blank(begin, end);
+    if (p0 >= end || (*p0 != '>' && *p0 != '@')) return false;
+    const bool fastq = *p0 == '@';
+    int n_pieces = 1;
+#ifdef _OPENMP
+    n_pieces = omp_get_max_threads();
+#endif
+    size_t piece_bytes = (size_t)1 << 25;
+    if (const char *env = getenv("APCH_PIECE_BYTES")) piece_bytes = std::max<size_t>(1, strtoull(env, nullptr, 10)); // tests
+    n_pieces = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_pieces * 4, size / piece_bytes));
+    std::vector<MapPiece> pieces((size_t)n_pieces);
+    const char *prev = p0;
+    for (int i = 0; i < n_pieces; i++) {
+        const char *next = end;
+        if (i + 1 < n_pieces) next = std::max(prev, next_record(begin, begin + size / (size_t)n_pieces * (size_t)(i + 1), end, fastq));
+        pieces[(size_t)i].begin = prev;
+        pieces[(size_t)i].end = next;
+        prev = next;
+    }
+    for (const MapPiece &pc : pieces)
+        if (pc.begin < pc.end && *pc.begin != (fastq ? '@' : '>')) return false; // boundary heuristic defeated
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < n_pieces; i++) parse_piece_mapped(pieces[(size_t)i], begin, fastq);
+    size_t total = 0;
+    for (const MapPiece &pc : pieces) {
+        if (!pc.ok || !pc.simple) return false;
+        total += pc.lens.size();
+    }
+    out.storage.reset();
+    out.starts.resize(total);
+    out.offsets.resize(total + 1);
+    uint64_t off = 0;
+    size_t r = 0;
+    for (const MapPiece &pc : pieces)
+        for (size_t j = 0; j < pc.lens.size(); j++) {
+            out.starts[r] = pc.starts[j];
+            out.offsets[r++] = off;
+            off += pc.lens[j];
+        }
+    out.offsets[total] = off;
+    out.n_bases = off;
+    out.mapping = std::move(mapping);
+    return true;
+}
+
 } // namespace
 
 bool read_fastx(const std::string &path, Reads &out, std::string &err) {
+    out.mapping.reset();
+    out.starts.clear();
+    if (read_fastx_mapped(path, out)) return true;
     FILE *f = fopen(path.c_str(), "rb");
     if (!f) {
         err = "could not open " + path;

@@ -45,13 +45,17 @@ bool parse_config(const std::string &path, std::vector<std::pair<std::string, st
 
 // :819-825 — all records of a FASTA/FASTQ file (ids and qualities dropped)
 struct Reads {
-    // the file's own buffer: sequences are compacted in place (no second copy of the data)
+    // Either the file's own buffer, sequences compacted in place (no second copy of the data) and read i at
+    // storage + offsets[i]; or — large files whose records keep their sequence on one line, e.g. 4-line FASTQ — the
+    // read-only mapping of the file itself, read i at mapping + starts[i] (no copy at all).
     std::unique_ptr<char[]> storage;
-    uint64_t n_bases = 0;          // bytes of `storage` that hold sequence letters (ASCII as read)
-    std::vector<uint64_t> offsets; // n+1
+    std::shared_ptr<const char> mapping; // unmapped by its deleter
+    uint64_t n_bases = 0;          // sequence letters (ASCII as read)
+    std::vector<uint64_t> offsets; // n+1 prefix sums of the read lengths
+    std::vector<uint64_t> starts;  // n file offsets (mapping mode only)
     uint64_t size() const { return offsets.empty() ? 0 : offsets.size() - 1; }
     uint64_t length(uint64_t i) const { return offsets[i + 1] - offsets[i]; }
-    const char *seq(uint64_t i) const { return storage.get() + offsets[i]; }
+    const char *seq(uint64_t i) const { return mapping ? mapping.get() + starts[i] : storage.get() + offsets[i]; }
 };
 bool read_fastx(const std::string &path, Reads &out, std::string &err);
 

@@ -24,6 +24,7 @@ HOST_SYMBOLS = {
     "apch_reads_count": (C.c_uint64, [_vp]),
     "apch_reads_length": (C.c_uint64, [_vp, C.c_uint64]),
     "apch_reads_seq": (_vp, [_vp, C.c_uint64]),
+    "apch_reads_mapped": (C.c_int, [_vp]),
     "apch_reads_free": (None, [_vp]),
     "apch_sample": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int64, _vp, _u64p]),
     "apch_synth_ends": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, _vp]),
@@ -107,6 +108,11 @@ class Reads:
 
     def __len__(self):
         return int(lib().apch_reads_count(self._h))
+
+    @property
+    def mapped(self):
+        """True when the reads are views into a mapping of the file (no copy was made)."""
+        return bool(lib().apch_reads_mapped(self._h))
 
     def seq(self, i):
         n = int(lib().apch_reads_length(self._h, i))

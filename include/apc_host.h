@@ -46,6 +46,9 @@ int apch_reads_load(const char *path, apch_reads **out);
 uint64_t apch_reads_count(const apch_reads *r);
 uint64_t apch_reads_length(const apch_reads *r, uint64_t i);
 const char *apch_reads_seq(const apch_reads *r, uint64_t i);
+/* 1 when the reads are views into a read-only mapping of the file (large files whose records keep their sequence
+ * on one line are parsed without copying), 0 when they were compacted into a buffer. */
+int apch_reads_mapped(const apch_reads *r);
 void apch_reads_free(apch_reads *r);
 
 /* :415-476 — shuffle read ids (std::shuffle over std::mt19937; seeded from

@@ -73,12 +73,15 @@ FASTA = ">r0 some id\nACGTACGTAC\nGGGG\n>r1\nacgtnnRYAC\n>r2\n\n>r3\nTTTT\n"
 FASTQ = "@r0\nACGTACGTACGGGG\n+\nIIIIIIIIIIIIII\n@r1\nacgtnnRYAC\n+r1\n@@@@>>>>++\n@r2\nTTTT\n+\n@III\n"
 
 
-def test_fasta_fastq_reader(host, tmp_path):
+@pytest.mark.parametrize("mmap_bytes", ["0", "1"])
+def test_fasta_fastq_reader(host, tmp_path, monkeypatch, mmap_bytes):
+    monkeypatch.setenv("APCH_MMAP_BYTES", mmap_bytes)   # 1: parse from a mapping of the file where its records allow it
     fa, fq = tmp_path / "x.fa", tmp_path / "x.fq"
     fa.write_text(FASTA)
     fq.write_text(FASTQ)
     r = host.Reads(fa)
     assert [r.seq(i) for i in range(len(r))] == [b"ACGTACGTACGGGG", b"acgtnnRYAC", b"", b"TTTT"]
+    assert not r.mapped                       # the fixture has a multi-line record
     r = host.Reads(fq)
     assert [r.seq(i) for i in range(len(r))] == [b"ACGTACGTACGGGG", b"acgtnnRYAC", b"TTTT"]
     with pytest.raises(OSError):
@@ -186,8 +189,9 @@ def _py_parse(text):
     return seqs
 
 
-@pytest.mark.parametrize("kind", ["fasta_multiline", "fastq_at_quality", "fasta_crlf"])
-def test_parallel_parser_pieces(host, tmp_path, kind, monkeypatch):
+@pytest.mark.parametrize("mmap_bytes", ["0", "1"])
+@pytest.mark.parametrize("kind", ["fasta_multiline", "fastq_at_quality", "fasta_crlf", "fasta_single", "fastq_crlf"])
+def test_parallel_parser_pieces(host, tmp_path, kind, monkeypatch, mmap_bytes):
     """The file is cut into pieces at record boundaries and compacted in place; tiny pieces
     force many cuts through multi-line records, CRLF and quality lines starting with '@'."""
     rng = np.random.default_rng(8)
@@ -200,6 +204,11 @@ def test_parallel_parser_pieces(host, tmp_path, kind, monkeypatch):
             recs.append(f">r{i} desc > @ +\n{body}\n" + ("\n" if i % 50 == 0 else ""))
         elif kind == "fasta_crlf":
             recs.append(f">r{i}\r\n{s}\r\n")
+        elif kind == "fasta_single":
+            recs.append(f">r{i} desc > @ +\n{s}\n" + ("\n" if i % 40 == 0 else ""))
+        elif kind == "fastq_crlf":
+            qual = "".join("@+>I#"[int(x)] for x in rng.integers(0, 5, n))
+            recs.append(f"@r{i}\r\n{s}\r\n+r{i}\r\n{qual}\r\n")
         else:
             qual = "".join("@+>I#"[int(x)] for x in rng.integers(0, 5, n))
             if n:
@@ -209,8 +218,12 @@ def test_parallel_parser_pieces(host, tmp_path, kind, monkeypatch):
     path = tmp_path / "x.fx"
     path.write_text(text, newline="")
     want = _py_parse(text)
+    # mmap_bytes 1: single-line records are parsed straight from a read-only mapping of the file (no copy);
+    # multi-line records make that path give way to the copying parser
+    monkeypatch.setenv("APCH_MMAP_BYTES", mmap_bytes)
     for piece in ("1000000000", "4096", "65536"):
         monkeypatch.setenv("APCH_PIECE_BYTES", piece)
         r = host.Reads(path)
         got = [r.seq(i).decode() for i in range(len(r))]
         assert got == want
+        assert r.mapped == (mmap_bytes == "1" and kind != "fasta_multiline")
