@@ -144,6 +144,8 @@ void apc_destroy(apc_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto &s : c->bs_streams) // a scan that failed half way may not have joined its side streams
+        if (s) cudaStreamSynchronize(s);
     cudaFree(c->d_tiles);
     cudaFree(c->d_lens);
     cudaFree(c->d_planes);
