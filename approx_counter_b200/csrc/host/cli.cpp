@@ -265,6 +265,10 @@ int cli_main(int argc, const char **argv) {
         for (uint64_t g = 0; g < n_gpus && create_status == APC_OK; g++)
             create_status = apc_create((int)(device0 + g), &gpus[g].ctx);
     });
+    struct Joiner { // an exception out of read_fastx (bad_alloc on a huge input) must not leave the thread joinable
+        std::thread &t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } creator_guard{creator};
 
     if (v > 0) print("Parsing FASTA file", tab_level); // :821-825
     Reads seqs;

@@ -9,12 +9,12 @@
 #include <fstream>
 #include <numeric>
 #include <random>
-#ifdef _OPENMP
-#include <omp.h>
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#ifdef _OPENMP
+#include <omp.h>
 #endif
 
 namespace apch {
@@ -256,6 +256,39 @@ void parse_piece(Piece &pc, bool fastq) {
     pc.n_bases = (uint64_t)(w - pc.begin);
 }
 
+// Read-only check that [begin, end) is a whole number of FASTQ records: every record starts with '@', has a
+// '+' line after its sequence lines and a quality string of exactly the sequence's length.  The boundary
+// heuristic of next_record can be defeated by wrapped (multi-line) records whose quality lines start with '@'
+// and '+'; a piece cut inside a record fails this check on either side of the cut, and the file is then parsed
+// in one piece (the in-place compaction of parse_piece cannot be undone, so the check runs first).
+bool verify_fastq_piece(const char *p, const char *end) {
+    while (true) {
+        p = skip_blank(p, end);
+        if (p >= end) return true;
+        if (*p != '@') return false;
+        p = line_end(p, end);
+        if (p < end) p++;
+        uint64_t n = 0;
+        while (p < end && *p != '+') {
+            const char *e = line_end(p, end), *t = e;
+            while (t > p && (t[-1] == '\r' || t[-1] == ' ' || t[-1] == '\t')) t--;
+            for (const char *c = p; c < t; c++) n += (*c != ' ' && *c != '\t' && *c != '\r');
+            p = e < end ? e + 1 : end;
+        }
+        if (p >= end) return false;
+        p = line_end(p, end);
+        if (p < end) p++;
+        uint64_t q = 0;
+        while (p < end && q < n) {
+            const char *e = line_end(p, end), *t = e;
+            while (t > p && t[-1] == '\r') t--;
+            q += (uint64_t)(t - p);
+            p = e < end ? e + 1 : end;
+        }
+        if (q != n) return false;
+    }
+}
+
 // first record start at or after `p` (a position inside the file)
 const char *next_record(const char *begin, const char *p, const char *end, bool fastq) {
     if (p <= begin) return begin;
@@ -326,6 +359,9 @@ void parse_piece_mapped(MapPiece &pc, const char *file_begin, bool fastq) {
                 q += (uint64_t)(t - p);
                 p = le < end ? le + 1 : end;
             }
+            // a quality string that is not exactly as long as the sequence means that this piece does not hold
+            // whole records (a cut inside a wrapped record): the copying parser re-checks and parses in one piece
+            if (q != n) { pc.ok = false; return; }
         }
         pc.starts.push_back((uint64_t)(s - file_begin));
         pc.lens.push_back(n);
@@ -465,8 +501,15 @@ bool read_fastx(const std::string &path, Reads &out, std::string &err) {
         // in-place compaction below cannot be undone, so unusual files (multi-line FASTQ whose
         // quality lines defeat the boundary heuristic) are detected first by a cheap check
         cut_pieces(n_pieces, pieces);
+        bool whole = true;
         for (const Piece &pc : pieces)
-            if (pc.begin < pc.end && *pc.begin != (fastq ? '@' : '>')) n_pieces = 1;
+            if (pc.begin < pc.end && *pc.begin != (fastq ? '@' : '>')) whole = false;
+        if (whole && fastq) {
+            const int n_chk = n_pieces;
+#pragma omp parallel for schedule(static, 1) reduction(&& : whole)
+            for (int i = 0; i < n_chk; i++) whole = whole && verify_fastq_piece(pieces[(size_t)i].begin, pieces[(size_t)i].end);
+        }
+        if (!whole) n_pieces = 1;
     }
     cut_pieces(n_pieces, pieces);
 #pragma omp parallel for schedule(static, 1)

@@ -227,3 +227,38 @@ def test_parallel_parser_pieces(host, tmp_path, kind, monkeypatch, mmap_bytes):
         got = [r.seq(i).decode() for i in range(len(r))]
         assert got == want
         assert r.mapped == (mmap_bytes == "1" and kind != "fasta_multiline")
+
+
+@pytest.mark.parametrize("mmap_bytes", ["0", "1"])
+def test_parallel_parser_multiline_fastq(host, tmp_path, monkeypatch, mmap_bytes):
+    """Wrapped (multi-line) FASTQ whose quality lines start with '@' and '+' defeats the 4-line boundary
+    heuristic; every piece is verified read-only before the in-place compaction and such files are parsed in
+    one piece.  Many small random files with tiny pieces (the advisor's reproduction)."""
+    monkeypatch.setenv("APCH_MMAP_BYTES", mmap_bytes)
+    bad = 0
+    for seed in range(120):
+        rng = np.random.default_rng(1000 + seed)
+        width = int(rng.integers(5, 40))
+        recs = []
+        for i in range(int(rng.integers(5, 60))):
+            n = int(rng.integers(0, 200))
+            s = "".join("ACGTN"[int(x)] for x in rng.integers(0, 5, n))
+            qual = "".join("@+@+I#"[int(x)] for x in rng.integers(0, 6, n))
+            wrap = lambda t: "\n".join(t[j:j + width] for j in range(0, max(len(t), 1), width))
+            if rng.random() < 0.3:
+                recs.append(f"@r{i}\n{s}\n+\n{qual}\n")      # some 4-line records in between
+            else:
+                recs.append(f"@r{i}\n{wrap(s)}\n+r{i}\n{wrap(qual)}\n")
+        text = "".join(recs)
+        path = tmp_path / f"m{seed}.fq"
+        path.write_text(text, newline="")
+        want = _py_parse(text)
+        for piece in ("16", "64", "700"):
+            monkeypatch.setenv("APCH_PIECE_BYTES", piece)
+            try:
+                r = host.Reads(path)
+                got = [r.seq(i).decode() for i in range(len(r))]
+            except OSError:
+                got = None
+            bad += got != want
+    assert bad == 0
