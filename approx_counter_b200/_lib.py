@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("APC_LIB_PATH") or os.path.join(_HERE, "csrc", "libapc
 APC_OK = 0
 ERRORS = {
     -1: "APC_ERR_INVALID", -2: "APC_ERR_CUDA", -3: "APC_ERR_NO_DEVICE", -4: "APC_ERR_NO_SAMPLE",
-    -5: "APC_ERR_NO_QUERIES", -6: "APC_ERR_NOMEM", -7: "APC_ERR_CAPACITY",
+    -5: "APC_ERR_NO_QUERIES", -6: "APC_ERR_NOMEM", -7: "APC_ERR_CAPACITY", -8: "APC_ERR_COMM",
 }
 
 # every symbol include/apc.h declares: (restype, argtypes)
@@ -26,6 +26,11 @@ class ApcTiming(C.Structure):
     _fields_ = [("upload_ms", C.c_float), ("exact_ms", C.c_float), ("scan_ms", C.c_float),
                 ("total_ms", C.c_float), ("scan_launches", C.c_uint64),
                 ("exact_launches", C.c_uint64)]
+
+
+class ApcScanStats(C.Structure):
+    _fields_ = [("scans", C.c_uint64), ("lop3_executed", C.c_double), ("lop3_top", C.c_double),
+                ("lop3_planned", C.c_double), ("lop3_one_kmer_per_warp", C.c_double)]
 
 
 SYMBOLS = {
@@ -58,6 +63,13 @@ SYMBOLS = {
     "apc_measure_int_peak": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double)]),
     "apc_microbench": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_double)]),
+    "apc_comm_unique_id": (C.c_int, [_vp]),
+    "apc_comm_init_rank": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "apc_comm_destroy": (C.c_int, [_vp]),
+    "apc_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "apc_allreduce_counts": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "apc_scan_allreduce": (C.c_int, [_vp, _vp]),
+    "apc_scan_stats_read": (C.c_int, [_vp, C.POINTER(ApcScanStats)]),
 }
 
 _lib = None

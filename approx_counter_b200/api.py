@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import ApcError, ApcTiming
+from ._lib import ApcError, ApcScanStats, ApcTiming
 
 
 def _as_kmers(kmers):
@@ -159,6 +159,43 @@ class ApproxCounter:
     def scan(self, d_counts_ptr=None):
         """Launch the scan on the context's stream (asynchronous)."""
         self._check(self._lib.apc_scan(self._h, C.c_void_p(int(d_counts_ptr) if d_counts_ptr else 0)))
+
+    # -- multi-GPU: one NCCL rank per context (apc_comm_*) ---------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128-byte id created on rank 0 and handed to every rank (any channel)."""
+        buf = (C.c_uint8 * 128)()
+        st = _lib.load().apc_comm_unique_id(buf)
+        if st != _lib.APC_OK:
+            raise ApcError(st, "apc_comm_unique_id (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def comm_init_rank(self, n_ranks, rank, unique_id):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._lib.apc_comm_init_rank(self._h, int(n_ranks), int(rank), buf))
+
+    def comm_destroy(self):
+        self._check(self._lib.apc_comm_destroy(self._h))
+
+    def comm_info(self):
+        r, n = C.c_int(), C.c_int()
+        self._check(self._lib.apc_comm_info(self._h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    def allreduce_counts(self, d_counts_ptr=None, n=0):
+        """In-place sum over the ranks on the context's stream (no-op without a communicator)."""
+        self._check(self._lib.apc_allreduce_counts(self._h, C.c_void_p(int(d_counts_ptr) if d_counts_ptr else 0), int(n)))
+
+    def scan_allreduce(self, d_counts_ptr=None):
+        """errorCount of a sharded sample: scan this rank's shard, then sum over the ranks (asynchronous)."""
+        self._check(self._lib.apc_scan_allreduce(self._h, C.c_void_p(int(d_counts_ptr) if d_counts_ptr else 0)))
+
+    def scan_stats(self):
+        """LOP3 warp instructions of the scans since the last call (apc_scan_stats_read); synchronises."""
+        s = ApcScanStats()
+        self._check(self._lib.apc_scan_stats_read(self._h, C.byref(s)))
+        return {"scans": int(s.scans), "lop3_executed": s.lop3_executed, "lop3_top": s.lop3_top,
+                "lop3_planned": s.lop3_planned, "lop3_one_kmer_per_warp": s.lop3_one_kmer_per_warp}
 
     def get_counts(self):
         out = np.zeros(self._n_kmers, np.uint64)

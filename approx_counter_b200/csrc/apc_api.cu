@@ -58,25 +58,31 @@ static float elapsed(cudaEvent_t a, cudaEvent_t b) {
 
 static int prepare_sample(Ctx *c, uint64_t n_reads, uint32_t max_len, uint64_t total_bases) {
     if (n_reads > 0xFFFFFFFFull * kTileReads) return fail(c, APC_ERR_INVALID, "too many reads");
-    c->n_reads = n_reads;
-    c->max_len = max_len;
-    c->total_bases = total_bases;
-    c->n_tiles = (uint32_t)((n_reads + kTileReads - 1) / kTileReads);
-    c->chunks = (max_len + kChunkBases - 1) / kChunkBases;
+    // the context holds no sample until every buffer of the new one exists (a failed call must not leave
+    // new sizes next to old buffers)
+    c->has_sample = false;
+    c->plan_gen++;
+    const uint32_t n_tiles = (uint32_t)((n_reads + kTileReads - 1) / kTileReads);
+    const uint32_t chunks = (max_len + kChunkBases - 1) / kChunkBases;
     // + one chunk of padding: the scan kernel always prefetches the next 512 bytes
-    const size_t tiles_bytes = ((size_t)c->n_tiles * c->chunks + 1) * kTileReads * sizeof(uint4);
+    const size_t tiles_bytes = ((size_t)n_tiles * chunks + 1) * kTileReads * sizeof(uint4);
     int st = grow(c, c->d_tiles, c->tiles_bytes, tiles_bytes);
     if (st) return st;
     // bit planes: 32 tiles per super-group, one uint4 per (column, tile), + two columns of padding at
     // either end for the kernels' prefetch (forward and backward walks)
-    const size_t n_sg = ((size_t)c->n_tiles + 31) / 32;
-    c->planes_bytes = n_sg * c->chunks * kChunkBases * 32 * sizeof(uint4);
-    if ((st = grow(c, c->d_planes, c->planes_cap, c->planes_bytes + 2 * apc::kBsPadCols * 32 * sizeof(uint4)))) return st;
-    const size_t lens_bytes = ((size_t)c->n_tiles * kTileReads + 1) * sizeof(uint32_t);
+    const size_t n_sg = ((size_t)n_tiles + 31) / 32;
+    const size_t planes_bytes = n_sg * chunks * kChunkBases * 32 * sizeof(uint4);
+    if ((st = grow(c, c->d_planes, c->planes_cap, planes_bytes + 2 * apc::kBsPadCols * 32 * sizeof(uint4)))) return st;
+    const size_t lens_bytes = ((size_t)n_tiles * kTileReads + 1) * sizeof(uint32_t);
     if ((st = grow(c, c->d_lens, c->lens_cap, lens_bytes))) return st;
     APC_CUDA(c, cudaMemsetAsync(c->d_lens, 0, lens_bytes, c->stream));
-    c->has_sample = true;
-    return APC_OK;
+    c->n_reads = n_reads;
+    c->max_len = max_len;
+    c->total_bases = total_bases;
+    c->n_tiles = n_tiles;
+    c->chunks = chunks;
+    c->planes_bytes = planes_bytes;
+    return APC_OK; // has_sample is set by the caller once the layout kernels are enqueued
 }
 
 } // namespace apc
@@ -97,6 +103,7 @@ const char *apc_strerror(int status) {
     case APC_ERR_NO_QUERIES: return "no queries set";
     case APC_ERR_NOMEM: return "out of memory";
     case APC_ERR_CAPACITY: return "output capacity too small";
+    case APC_ERR_COMM: return "communicator (NCCL) error";
     default: return "unknown status";
     }
 }
@@ -121,11 +128,13 @@ int apc_create(int device, apc_ctx **out) {
     c->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 6 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_table, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_job_counter, (apc::kBsShapes + 1) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(c->d_job_counter, 0, (apc::kBsShapes + 1) * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_deep_lop3, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(c->d_deep_lop3, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->bs_fork, cudaEventDisableTiming);
     for (int i = 0; i < apc::kBsShapes && e == cudaSuccess; i++) {
         e = cudaStreamCreateWithFlags(&c->bs_streams[i], cudaStreamNonBlocking);
@@ -153,6 +162,9 @@ void apc_destroy(apc_ctx *c) {
     cudaFree(c->d_peq);
     cudaFree(c->d_counts);
     cudaFree(c->d_job_counter);
+    cudaFree(c->d_deep_lop3);
+    if (c->scan_graph) cudaGraphExecDestroy(c->scan_graph);
+    apc_comm_destroy(c);
     cudaFree(c->d_stage);
     cudaFree(c->d_stage_offs);
     apc::free_exact_scratch(c);
@@ -198,6 +210,7 @@ int apc_upload_sample_async(apc_ctx *c, const uint8_t *bases, uint64_t n_reads, 
                                                 c->d_tiles, c->d_lens, c->stream));
     APC_CUDA(c, apc::launch_build_planes(*c));
     APC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    c->has_sample = true;
     c->timing.upload_ms = -1.f; // resolved lazily by apc_last_timing
     return APC_OK;
 }
@@ -251,6 +264,7 @@ int apc_upload_sample_ragged(apc_ctx *c, const uint8_t *bases, const uint64_t *o
     APC_CUDA(c, apc::launch_build_planes(*c));
     APC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->has_sample = true;
     c->timing.upload_ms = apc::elapsed(c->ev[0], c->ev[1]);
     return APC_OK;
     APC_CATCH(c)
@@ -307,6 +321,7 @@ int apc_exact_solid(apc_ctx *c, uint8_t k, float lc_adjusted, uint64_t solid_km,
 }
 
 int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kmers) {
+    APC_TRY
     int st = apc::bind(c);
     if (st) return st;
     if (k < 2 || k > 32) return apc::fail(c, APC_ERR_INVALID, "k must be in [2,32]");
@@ -315,13 +330,16 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
     if (k < 32)
         for (uint32_t i = 0; i < n_kmers; i++)
             if (kmers[i] >> (2 * k)) return apc::fail(c, APC_ERR_INVALID, "k-mer value wider than 2k bits");
-    c->k = k;
-    c->n_kmers = n_kmers;
-    c->variant = apc::pick_variant(k, c->opt_variant);
+    // Everything is staged in locals and published to the context only after every allocation has
+    // succeeded; until then the context has no queries (k = 0), so a failed call cannot leave new sizes
+    // next to old buffers.
+    c->k = 0;
+    c->plan_gen++;
+    const apc::ScanVariant variant = apc::pick_variant(k, c->opt_variant);
     // the match tables are built in a context-owned pinned buffer so that the H2D copy is
     // truly asynchronous; the buffer is only rewritten once its previous copy has completed
-    const uint32_t qg = c->variant.queries_per_group();
-    const bool bs = c->variant.bitslice();
+    const uint32_t qg = variant.queries_per_group();
+    const bool bs = variant.bitslice();
     // row-packed kernels take match tables, the bit-sliced kernel the k-mers themselves
     const size_t table_words = bs ? (size_t)n_kmers * 3 : (size_t)((n_kmers + qg - 1) / qg) * apc::kPeqRows * apc::kWordsPerThread;
     if (c->table_copy_pending) {
@@ -338,28 +356,30 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
         c->pinned_cap = cap;
     }
     void *d_dst = nullptr;
+    uint32_t n_groups = 0;
+    uint32_t units[apc::kBsShapes] = {};
     if (bs) {
         // k-mers in scan order (units of prefix- or suffix-sharing k-mers first, shape by shape), then the
         // index of each in the caller's order; bit 31 marks the members of a unit that is scanned backwards
         std::vector<uint32_t> order;
         std::vector<uint8_t> reversed;
-        apc::bs_group_queries(kmers, n_kmers, k, c->variant.pairing() ? c->opt_shape_mask : 0u, (float)c->opt_alive_pct / 100.f,
-                              order, reversed, c->bs_units);
+        apc::bs_group_queries(kmers, n_kmers, k, variant.pairing() ? c->opt_shape_mask : 0u, (float)c->opt_alive_pct / 100.f,
+                              order, reversed, units);
         uint64_t *hk = (uint64_t *)c->h_pinned;
         uint32_t *hp = (uint32_t *)(hk + n_kmers);
         for (uint32_t i = 0; i < n_kmers; i++) {
             hk[i] = reversed[i] ? apc::bs_reverse_kmer(kmers[order[i]], k) : kmers[order[i]];
             hp[i] = order[i] | (reversed[i] ? 0x80000000u : 0u);
         }
-        c->n_groups = n_kmers;
+        n_groups = n_kmers;
         if ((st = apc::grow(c, c->d_kmers, c->kmers_cap, table_words * sizeof(uint32_t)))) return st;
         d_dst = c->d_kmers;
     } else {
-        apc::build_peq_tables(kmers, n_kmers, k, c->variant, (uint32_t *)c->h_pinned, c->n_groups);
+        apc::build_peq_tables(kmers, n_kmers, k, variant, (uint32_t *)c->h_pinned, n_groups);
         if ((st = apc::grow(c, c->d_peq, c->peq_cap, table_words * sizeof(uint32_t)))) return st;
         d_dst = c->d_peq;
     }
-    const size_t slots = (size_t)c->n_groups * qg;
+    const size_t slots = (size_t)n_groups * qg;
     if ((st = apc::grow(c, c->d_counts, c->counts_cap, slots * sizeof(unsigned long long)))) return st;
     if (table_words) {
         APC_CUDA(c, cudaMemcpyAsync(d_dst, c->h_pinned, table_words * sizeof(uint32_t), cudaMemcpyHostToDevice,
@@ -367,7 +387,13 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
         APC_CUDA(c, cudaEventRecord(c->ev_table, c->stream));
         c->table_copy_pending = true;
     }
+    c->n_kmers = n_kmers;
+    c->variant = variant;
+    c->n_groups = n_groups;
+    for (int i = 0; i < apc::kBsShapes; i++) c->bs_units[i] = units[i];
+    c->k = k;
     return APC_OK;
+    APC_CATCH(c)
 }
 
 int apc_plan_queries(uint8_t k, const uint64_t *kmers, uint32_t n_kmers, uint32_t *order_out, uint8_t *reversed_out,
@@ -395,6 +421,79 @@ int apc_plan_queries(uint8_t k, const uint64_t *kmers, uint32_t n_kmers, uint32_
     return APC_OK;
 }
 
+// The launches of one scan, directly or as a replay of their CUDA graph.  A scan that is issued a second time
+// unchanged (same sample, queries, options, destination and stream) is captured while it is launched —
+// stream capture follows the fork/join events onto the side streams — and replayed from then on: one
+// cudaGraphLaunch instead of up to 13 kernel launches and 24 event calls, which is most of a C1-sized scan.
+static int scan_launches(apc_ctx *c, unsigned long long *dst) {
+    const bool same = c->opt_graph && c->variant.bitslice() && c->last_scan_gen == c->plan_gen &&
+                      c->last_scan_dst == dst && c->last_scan_stream == c->stream;
+    c->last_scan_gen = c->plan_gen;
+    c->last_scan_dst = dst;
+    c->last_scan_stream = c->stream;
+    if (same && c->scan_graph && c->graph_gen == c->plan_gen && c->graph_dst == dst && c->graph_stream == c->stream) {
+        APC_CUDA(c, cudaGraphLaunch(c->scan_graph, c->stream));
+        c->timing.scan_launches = c->graph_launches;
+        // the plan's share of the statistics (the kernels tally the data-dependent part themselves)
+        c->stat_scans++;
+        c->stat_lop3_top += c->graph_lop3[0];
+        c->stat_lop3_all += c->graph_lop3[1];
+        c->stat_lop3_single += c->graph_lop3[2];
+        return APC_OK;
+    }
+    if (!same) {
+        APC_CUDA(c, apc::launch_scan(*c, dst, &c->timing.scan_launches));
+        return APC_OK;
+    }
+    // second identical scan: capture it (nothing runs during capture), then launch the graph
+    if (c->scan_graph) {
+        cudaGraphExecDestroy(c->scan_graph);
+        c->scan_graph = nullptr;
+        c->graph_gen = ~0ull;
+    }
+    const double before[3] = {c->stat_lop3_top, c->stat_lop3_all, c->stat_lop3_single};
+    const uint64_t scans_before = c->stat_scans;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { // the stream cannot be captured (e.g. the legacy default stream): launch directly
+        cudaGetLastError();
+        c->opt_graph = 0;
+        APC_CUDA(c, apc::launch_scan(*c, dst, &c->timing.scan_launches));
+        return APC_OK;
+    }
+    const cudaError_t le = apc::launch_scan(*c, dst, &c->timing.scan_launches);
+    e = cudaStreamEndCapture(c->stream, &graph);
+    if (le != cudaSuccess || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        c->opt_graph = 0; // do not try again on this context
+        c->stat_scans = scans_before;
+        c->stat_lop3_top = before[0]; c->stat_lop3_all = before[1]; c->stat_lop3_single = before[2];
+        APC_CUDA(c, apc::launch_scan(*c, dst, &c->timing.scan_launches));
+        return APC_OK;
+    }
+    e = cudaGraphInstantiate(&c->scan_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        c->scan_graph = nullptr;
+        cudaGetLastError();
+        c->opt_graph = 0;
+        c->stat_scans = scans_before;
+        c->stat_lop3_top = before[0]; c->stat_lop3_all = before[1]; c->stat_lop3_single = before[2];
+        APC_CUDA(c, apc::launch_scan(*c, dst, &c->timing.scan_launches));
+        return APC_OK;
+    }
+    c->graph_gen = c->plan_gen;
+    c->graph_dst = dst;
+    c->graph_stream = c->stream;
+    c->graph_launches = c->timing.scan_launches;
+    c->graph_lop3[0] = c->stat_lop3_top - before[0];
+    c->graph_lop3[1] = c->stat_lop3_all - before[1];
+    c->graph_lop3[2] = c->stat_lop3_single - before[2];
+    APC_CUDA(c, cudaGraphLaunch(c->scan_graph, c->stream));
+    return APC_OK;
+}
+
 int apc_scan(apc_ctx *c, uint64_t *d_counts) {
     int st = apc::bind(c);
     if (st) return st;
@@ -402,9 +501,33 @@ int apc_scan(apc_ctx *c, uint64_t *d_counts) {
     if (c->k == 0) return apc::fail(c, APC_ERR_NO_QUERIES, "apc_scan: no queries");
     unsigned long long *dst = d_counts ? (unsigned long long *)d_counts : c->d_counts;
     APC_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    APC_CUDA(c, apc::launch_scan(*c, dst, &c->timing.scan_launches));
+    if ((st = scan_launches(c, dst))) return st;
     APC_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     c->timing.scan_ms = -1.f; // resolved lazily by apc_last_timing / apc_get_counts
+    return APC_OK;
+}
+
+int apc_scan_allreduce(apc_ctx *c, uint64_t *d_counts) {
+    int st = apc_scan(c, d_counts);
+    if (st) return st;
+    return apc_allreduce_counts(c, d_counts, c->n_kmers);
+}
+
+int apc_scan_stats_read(apc_ctx *c, apc_scan_stats *out) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (!out) return apc::fail(c, APC_ERR_INVALID, "NULL argument");
+    unsigned long long deep = 0;
+    APC_CUDA(c, cudaMemcpyAsync(&deep, c->d_deep_lop3, sizeof deep, cudaMemcpyDeviceToHost, c->stream));
+    APC_CUDA(c, cudaMemsetAsync(c->d_deep_lop3, 0, sizeof deep, c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    out->scans = c->stat_scans;
+    out->lop3_top = c->stat_lop3_top;
+    out->lop3_executed = c->stat_lop3_top + (double)deep;
+    out->lop3_planned = c->stat_lop3_all;
+    out->lop3_one_kmer_per_warp = c->stat_lop3_single;
+    c->stat_scans = 0;
+    c->stat_lop3_top = c->stat_lop3_all = c->stat_lop3_single = 0.;
     return APC_OK;
 }
 
@@ -460,6 +583,11 @@ int apc_last_timing(const apc_ctx *cc, apc_timing *out) {
 
 int apc_set_option(apc_ctx *c, const char *name, int64_t value) {
     if (!c || !name) return APC_ERR_INVALID;
+    c->plan_gen++; // any option may change what a scan launches
+    if (!std::strcmp(name, "scan_graph")) {
+        c->opt_graph = value != 0;
+        return APC_OK;
+    }
     if (!std::strcmp(name, "scan_variant")) {
         if (value != 0 && value != 1 && value != 2 && value != 3 && value != 6 && value != 7 && value != 8)
             return apc::fail(c, APC_ERR_INVALID, "scan_variant must be 0,1,2,3,6,7 or 8");

@@ -102,7 +102,7 @@ struct Ctx {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // upload 0-1, scan 2-3, approx 4-5
+    cudaEvent_t ev[8] = {}; // upload 0-1, scan 2-3, approx 4-5, exact stage 6-7
     cudaEvent_t ev_table = nullptr; // completion of the last match-table copy out of h_pinned
     bool table_copy_pending = false;
     std::string err;
@@ -139,9 +139,30 @@ struct Ctx {
     size_t counts_cap = 0;
     unsigned int *d_job_counter = nullptr;  // job queue heads of the persistent scan kernels (self re-arming), one per
                                             // concurrent launch: [kBsShapes + 1]
+    unsigned long long *d_deep_lop3 = nullptr; // LOP3 warp instructions the scan kernels spent on deep rows (dead-row
+                                               // skipping makes that data dependent) since the last apc_scan_stats_read
+    // host side of the same statistics, accumulated per scan from the plan
+    mutable double stat_lop3_top = 0., stat_lop3_all = 0., stat_lop3_single = 0.;
+    mutable uint64_t stat_scans = 0;
     cudaStream_t bs_streams[kBsShapes] = {}; // side streams of the bit-sliced scan (one launch per shape, concurrent)
     cudaEvent_t bs_join[kBsShapes] = {};
     cudaEvent_t bs_fork = nullptr;
+
+    // CUDA graph of the launches of one scan (fork, one kernel per shape in use, join): captured when the same
+    // scan is issued a second time, replayed afterwards — a C1-sized scan is launch-bound otherwise
+    cudaGraphExec_t scan_graph = nullptr;
+    uint64_t plan_gen = 0;          // bumped by every upload / set_queries / option change that affects a scan
+    uint64_t graph_gen = ~0ull;     // plan_gen the graph was captured for (~0 = none)
+    uint64_t last_scan_gen = ~0ull; // plan_gen of the previous scan
+    unsigned long long *graph_dst = nullptr, *last_scan_dst = nullptr;
+    cudaStream_t graph_stream = nullptr, last_scan_stream = nullptr;
+    uint64_t graph_launches = 0;
+    double graph_lop3[3] = {0., 0., 0.}; // the plan statistics of one replay (top, all, one k-mer per warp)
+    int opt_graph = 1; // 0 = never capture
+
+    // multi-GPU: an NCCL communicator (one rank per context), libnccl loaded on first use (apc_comm.cpp)
+    void *nccl_comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
 
     // staging
     uint8_t *d_stage = nullptr;

@@ -80,6 +80,18 @@ __device__ __forceinline__ void bs_rows(uint32_t (&r0)[N], uint32_t (&r1)[N], ui
 // deep rows + a vote only on the first quiet column after a busy stretch.
 constexpr int bs_check_row(int k) { return bs_check_row_host(k); } // apc_internal.h (the planner needs it too)
 
+// Rows of a unit (trunk of P rows + G tails of K - P rows; P = K, G = 1: a single k-mer) that are computed in every
+// column (top) and only where something can reach them (deep), and the columns one dead-row test covers.
+struct BsRowSplit {
+    int top, deep, cols_per_test;
+};
+__host__ __device__ constexpr BsRowSplit bs_rows_split(int k, int p, int g, int m) {
+    const int t = k - p, rows = p + g * t;
+    if (m >= k) return BsRowSplit{rows, 0, 2};
+    if (m <= p) return BsRowSplit{m, rows - m, 2};          // one test per column pair
+    return BsRowSplit{p + g * (m - p), g * (k - m), 1};     // split inside the tails: one test per column
+}
+
 template <int N, int FIRST>
 __device__ __forceinline__ void bs_rows_init(uint32_t (&r0)[N], uint32_t (&r1)[N], uint32_t (&r2)[N]) {
     const uint32_t ALL = 0xFFFFFFFFu;
@@ -161,7 +173,7 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
                const uint32_t read_len, const uint64_t range_lo, const uint64_t range_hi,
                const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ perm, const uint32_t n_units,
                const uint32_t sg_per_job, const uint32_t n_jobs, unsigned long long *__restrict__ counts,
-               unsigned int *__restrict__ job_counter) {
+               unsigned int *__restrict__ job_counter, unsigned long long *__restrict__ deep_lop3) {
     __shared__ __align__(16) uint32_t s_mask[2][4 * kGroupsPerSuper];
     const uint32_t lane = threadIdx.x;
     const uint32_t pairs = (read_len + 1) / 2; // an odd length is rounded up with one padding column (N: matches nothing)
@@ -176,6 +188,7 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
         for (int i = 0; i < K; i++) off[i] = (uint32_t)((kmer >> (2 * (K - 1 - i))) & 3u) * kPlaneRow;
 
         uint32_t cnt = 0;
+        uint32_t n_run = 0; // dead-row tests of this job after which the deep rows were computed (apc_scan_stats_read)
         const uint32_t sg_end = min(n_sg, (jb + 1) * sg_per_job);
         for (uint32_t sg = jb * sg_per_job; sg < sg_end; sg++) {
             uint32_t r0[K], r1[K], r2[K];
@@ -212,6 +225,7 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
                         run = __any_sync(0xFFFFFFFFu, z != 0);
                     }
                     deep_zero = !run;
+                    n_run += run;
                     APC_BS_STAT(run);
                     if (run) {
                         bs_rows<K, 0, true, M, K>(r0, r1, r2, ca, slot_a, off);
@@ -227,6 +241,9 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
         }
         const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, cnt);
         if (lane == 0 && total) atomicAdd(&counts[__ldg(perm + u)], (unsigned long long)total);
+        // LOP3 (warp instructions) spent on deep rows by this job: one test per column pair, 5 per row and column
+        constexpr int kDeepLop3PerTest = 2 * 5 * bs_rows_split(K, K, 1, M).deep;
+        if (lane == 0 && n_run) atomicAdd(deep_lop3, (unsigned long long)n_run * kDeepLop3PerTest);
     }
 }
 
@@ -245,7 +262,7 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                 const uint32_t read_len, const uint64_t range_lo, const uint64_t range_hi,
                 const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ perm, const uint32_t n_units,
                 const uint32_t sg_per_job, const uint32_t n_jobs, unsigned long long *__restrict__ counts,
-                unsigned int *__restrict__ job_counter) {
+                unsigned int *__restrict__ job_counter, unsigned long long *__restrict__ deep_lop3) {
     constexpr int T = K - P; // rows of the private tails
     static_assert(P >= 2 && T >= 1, "the always-matching rows 0..1 must lie in the shared part");
     __shared__ __align__(16) uint32_t s_mask[2][4 * kGroupsPerSuper];
@@ -275,6 +292,7 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
         uint32_t cnt[G];
 #pragma unroll
         for (int g = 0; g < G; g++) cnt[g] = 0;
+        uint32_t n_run = 0; // dead-row tests of this job after which the deep rows were computed (apc_scan_stats_read)
         const uint32_t sg_end = min(n_sg, (jb + 1) * sg_per_job);
         for (uint32_t sg = jb * sg_per_job; sg < sg_end; sg++) {
             uint32_t s0[P], s1[P], s2[P], x0[G][T], x1[G][T], x2[G][T];
@@ -313,6 +331,7 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                         run = __any_sync(0xFFFFFFFFu, z != 0);
                     }
                     deep_zero = !run;
+                    n_run += run;
                     APC_BS_STAT(run);
                     if (run) {
                         bs_rows<P, 0, false, M, P>(s0, s1, s2, ca, slot_a, off_s);
@@ -363,7 +382,8 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                             run = __any_sync(0xFFFFFFFFu, z != 0);
                         }
                         deep_zero = !run;
-                        APC_BS_STAT(run);
+                        n_run += run;
+                    APC_BS_STAT(run);
                         if (run) {
 #pragma unroll
                             for (int g = 0; g < G; g++) bs_rows<T, P, true, S, T>(x0[g], x1[g], x2[g], cg[g], slot, off_t[g]);
@@ -384,6 +404,10 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
             if (lane == 0 && t)
                 atomicAdd(&counts[__ldg(perm + (size_t)G * u + g) & 0x7FFFFFFFu], (unsigned long long)t);
         }
+        if (lane == 0 && n_run) {
+            constexpr int kDeepLop3PerTest = bs_rows_split(K, P, G, M).cols_per_test * 5 * bs_rows_split(K, P, G, M).deep;
+            atomicAdd(deep_lop3, (unsigned long long)n_run * kDeepLop3PerTest);
+        }
     }
 }
 
@@ -397,6 +421,8 @@ struct BsLaunchCtx {
     uint32_t sg_per_job_opt; // 0 = choose per launch
     uint64_t *launches;
     int slot; // next stream / job counter
+    // LOP3 warp instructions of this scan: in the rows computed in every column, and in all rows if nothing were skipped
+    double lop3_top = 0., lop3_all = 0.;
 };
 
 inline uint32_t bs_sg_per_job(const BsLaunchCtx &l, uint32_t n_units, int mb) {
@@ -408,8 +434,14 @@ inline uint32_t bs_sg_per_job(const BsLaunchCtx &l, uint32_t n_units, int mb) {
 }
 
 template <typename Kernel>
-static cudaError_t bs_launch_one(BsLaunchCtx &l, Kernel kernel, int mb, uint32_t first_kmer, uint32_t n_units) {
+static cudaError_t bs_launch_one(BsLaunchCtx &l, Kernel kernel, int mb, uint32_t first_kmer, uint32_t n_units,
+                                 const BsRowSplit split) {
     const Ctx &c = *l.c;
+    {   // rows 0 and 1 hold constants at levels 1 and 2: 7 LOP3 fewer than 5 per row (bs_rows)
+        const double unit_cols = (double)n_units * l.r.n_sg * (2 * ((c.max_len + 1) / 2));
+        l.lop3_top += unit_cols * (5 * split.top - 7);
+        l.lop3_all += unit_cols * (5 * (split.top + split.deep) - 7);
+    }
     const uint32_t spj = bs_sg_per_job(l, n_units, mb);
     const uint64_t jobs = (uint64_t)((l.r.n_sg + spj - 1) / spj) * n_units;
     if (jobs > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
@@ -424,7 +456,7 @@ static cudaError_t bs_launch_one(BsLaunchCtx &l, Kernel kernel, int mb, uint32_t
     }
     kernel<<<grid, 32, 0, s>>>(c.planes(), l.r.sg_first, l.r.n_sg, c.chunks * kChunkBases, c.max_len, l.r.lo, l.r.hi,
                               c.d_kmers + first_kmer, perm + first_kmer, n_units, spj, (uint32_t)jobs, l.d_counts,
-                              c.d_job_counter + slot);
+                              c.d_job_counter + slot, c.d_deep_lop3);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     (*l.launches)++;
     if (slot > 0) { // join
@@ -442,7 +474,8 @@ static cudaError_t bs_launch_shapes(BsLaunchCtx &l, uint32_t &first_kmer) {
             const uint32_t n_units = l.c->bs_units[S];
             if (n_units) {
                 constexpr int MB = bs_warps_per_sm_c(K - sh.t + sh.g * sh.t);
-                cudaError_t e = bs_launch_one(l, bs_group_kernel<K, K - sh.t, sh.g, MB>, MB, first_kmer, n_units);
+                cudaError_t e = bs_launch_one(l, bs_group_kernel<K, K - sh.t, sh.g, MB>, MB, first_kmer, n_units,
+                                              bs_rows_split(K, K - sh.t, sh.g, bs_check_row(K)));
                 if (e != cudaSuccess) return e;
                 first_kmer += n_units * sh.g;
             }
@@ -464,7 +497,7 @@ static cudaError_t launch_bs_k(BsLaunchCtx &l) {
         // registers: 3K of state + the row masks of two columns in flight (ptxas wants about 6K + 26);
         // CTAs (= warps) per SM chosen so that nothing spills
         constexpr int MB = bs_warps_per_sm_c(K);
-        e = bs_launch_one(l, bs_scan_kernel<K, MB>, MB, first, c.n_kmers - first);
+        e = bs_launch_one(l, bs_scan_kernel<K, MB>, MB, first, c.n_kmers - first, bs_rows_split(K, K, 1, bs_check_row(K)));
     }
     return e;
 }

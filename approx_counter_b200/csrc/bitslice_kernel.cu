@@ -293,11 +293,17 @@ cudaError_t launch_bs_scan(const Ctx &c, uint64_t lo, uint64_t hi, unsigned long
     cudaError_t e = cudaEventRecord(c.bs_fork, c.stream);
     if (e != cudaSuccess) return e;
     switch (c.k & 3) { // the instantiations are spread over four objects by k mod 4 (bitslice_part.cu)
-    case 0: return launch_bs_part0(l);
-    case 1: return launch_bs_part1(l);
-    case 2: return launch_bs_part2(l);
-    default: return launch_bs_part3(l);
+    case 0: e = launch_bs_part0(l); break;
+    case 1: e = launch_bs_part1(l); break;
+    case 2: e = launch_bs_part2(l); break;
+    default: e = launch_bs_part3(l); break;
     }
+    // statistics (apc_scan_stats_read): what this scan costs on the ALU pipe according to its plan
+    c.stat_scans++;
+    c.stat_lop3_top += l.lop3_top;
+    c.stat_lop3_all += l.lop3_all;
+    c.stat_lop3_single += (double)c.n_kmers * l.r.n_sg * (2 * ((c.max_len + 1) / 2)) * (5 * c.k - 7);
+    return e;
 }
 
 } // namespace apc

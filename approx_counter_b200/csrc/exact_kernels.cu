@@ -725,7 +725,7 @@ int exact_count_select(Ctx *c, uint8_t k, float lc_adjusted, uint64_t lim, uint6
                        std::vector<uint64_t> &kmers, std::vector<uint64_t> &counts, uint64_t *n_needed,
                        uint64_t *n_distinct, uint64_t *n_had_n) {
     const uint32_t lc_min_sum = apch::lc_min_filtered_sum(k, lc_adjusted);
-    cudaEvent_t e0 = c->ev[0], e1 = c->ev[1];
+    cudaEvent_t e0 = c->ev[6], e1 = c->ev[7];
     APC_CUDA(c, cudaEventRecord(e0, c->stream));
     int st = k <= 16 ? run_exact<uint32_t>(c, k, lc_min_sum, lim, solid_km, forbidden, n_forbidden, capacity, kmers,
                                            counts, n_needed, n_distinct, n_had_n)

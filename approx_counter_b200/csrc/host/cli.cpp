@@ -283,6 +283,29 @@ int cli_main(int argc, const char **argv) {
         }
     }
     apc_ctx *ctx0 = gpus[0].ctx;
+    // several GPUs: the contexts form one NCCL communicator, one rank each (apc_comm_*, include/apc.h)
+    bool have_comm = false;
+    if (n_gpus > 1) {
+        uint8_t id[APC_COMM_ID_BYTES];
+        int st = apc_comm_unique_id(id);
+        if (st == APC_OK) {
+            std::vector<int> status(n_gpus, APC_OK);
+            std::vector<std::thread> joiners;
+            for (uint64_t g = 0; g < n_gpus; g++)
+                joiners.emplace_back([&, g]() { status[g] = apc_comm_init_rank(gpus[g].ctx, (int)n_gpus, (int)g, id); });
+            for (auto &t : joiners) t.join();
+            have_comm = true;
+            for (uint64_t g = 0; g < n_gpus; g++)
+                if (status[g] != APC_OK) { have_comm = false; st = status[g]; }
+        }
+        if (!have_comm) {
+            std::cerr << warning << "no NCCL communicator (" << apc_strerror(st) << ": " << apc_last_error(ctx0)
+                      << "); the per-GPU count vectors are summed on the host" << std::endl;
+            for (uint64_t g = 0; g < n_gpus; g++) apc_comm_destroy(gpus[g].ctx);
+        } else if (v > 1) {
+            print("NCCL communicator over " + std::to_string(n_gpus) + " GPUs", tab_level);
+        }
+    }
     if (v > 0) print("Number of sequences found: " + std::to_string(seqs.size()) + ".", tab_level);
 
     std::string run_suffix;
@@ -359,29 +382,40 @@ int cli_main(int argc, const char **argv) {
                 st = apc_approx_count(ctx0, (uint8_t)k, km.data(), (uint32_t)n_top, approx.data());
                 if (st != APC_OK) return gpu_fail("approximate k-mer count", ctx0, st);
             } else {
-                // shard the sampled reads over the GPUs (32-read tiles), scan every shard for all
-                // k-mers concurrently, sum the per-GPU count vectors
+                // Shard the sampled reads over the GPUs (contiguous blocks of 32-read tiles), one host thread per
+                // GPU: upload the shard (GPU 0 already holds the whole sample for the exact stage and scans a
+                // sub-range of it), scan it for all k-mers, sum the count vectors with one ncclAllReduce issued
+                // through the C ABI (apc_scan_allreduce).  Without a communicator the vectors are summed here.
                 const uint64_t tiles = (n_sampled + 31) / 32, per = (tiles + n_gpus - 1) / n_gpus;
-                std::vector<std::vector<uint64_t>> part(n_gpus, std::vector<uint64_t>(n_top, 0));
-                for (uint64_t g = 0; g < n_gpus; g++) {
-                    const uint64_t first = std::min(n_sampled, g * per * 32), last = std::min(n_sampled, (g + 1) * per * 32);
-                    apc_ctx *c = gpus[g].ctx;
-                    if (g == 0) {
-                        apc_set_option(c, "scan_first_read", (int64_t)first);
-                        apc_set_option(c, "scan_n_reads", (int64_t)(last - first));
-                    } else {
-                        st = apc_upload_sample(c, sample.data() + first * row_len, last - first, row_len);
-                        if (st != APC_OK) return gpu_fail("uploading a shard", c, st);
-                    }
-                    if ((st = apc_set_queries(c, (uint8_t)k, km.data(), (uint32_t)n_top)) != APC_OK ||
-                        (st = apc_scan(c, nullptr)) != APC_OK)
-                        return gpu_fail("approximate k-mer count", c, st);
-                }
-                for (uint64_t g = 0; g < n_gpus; g++) {
-                    if ((st = apc_get_counts(gpus[g].ctx, part[g].data())) != APC_OK)
-                        return gpu_fail("reading counts", gpus[g].ctx, st);
+                std::vector<int> status(n_gpus, APC_OK);
+                std::vector<std::vector<uint64_t>> part(n_gpus);
+                std::vector<std::thread> workers;
+                for (uint64_t g = 0; g < n_gpus; g++)
+                    workers.emplace_back([&, g]() {
+                        const uint64_t first = std::min(n_sampled, g * per * 32), last = std::min(n_sampled, (g + 1) * per * 32);
+                        apc_ctx *c = gpus[g].ctx;
+                        int s = APC_OK;
+                        if (g == 0) {
+                            apc_set_option(c, "scan_first_read", (int64_t)first);
+                            apc_set_option(c, "scan_n_reads", (int64_t)(last - first));
+                        } else {
+                            s = apc_upload_sample_async(c, sample.data() + first * row_len, last - first, row_len);
+                        }
+                        if (s == APC_OK) s = apc_set_queries(c, (uint8_t)k, km.data(), (uint32_t)n_top);
+                        if (s == APC_OK) s = have_comm ? apc_scan_allreduce(c, nullptr) : apc_scan(c, nullptr);
+                        if (s == APC_OK && (g == 0 || !have_comm)) {
+                            part[g].assign(n_top, 0);
+                            s = apc_get_counts(c, part[g].data());
+                        } else if (s == APC_OK) {
+                            s = apc_sync(c);
+                        }
+                        status[g] = s;
+                    });
+                for (auto &t : workers) t.join();
+                for (uint64_t g = 0; g < n_gpus; g++)
+                    if (status[g] != APC_OK) return gpu_fail("approximate k-mer count", gpus[g].ctx, status[g]);
+                for (uint64_t g = 0; g < (have_comm ? 1 : n_gpus); g++)
                     for (uint64_t i = 0; i < n_top; i++) approx[i] += part[g][i];
-                }
                 apc_set_option(ctx0, "scan_first_read", 0);
                 apc_set_option(ctx0, "scan_n_reads", -1);
             }

@@ -5,7 +5,9 @@ count vectors are summed with one small all-reduce.
 The reference's only parallelism is an OpenMP team over k-mers sharing one index
 (/root/reference/approx_counter.cpp:547-599); reads are independent and the
 result is a sum over reads (:589-596), so sharding reads needs no other exchange.
-torch.distributed is plumbing only (NCCL over NVLink on GPUs, gloo in CPU tests).
+On GPUs the all-reduce is libapc's own (apc_comm_init_rank + apc_scan_allreduce, include/apc.h: one
+ncclAllReduce on the context's stream); torch.distributed only carries the communicator's id to the ranks.
+CPU tests of the host logic run the same class over gloo with torch's all-reduce.
 """
 import numpy as np
 
@@ -48,6 +50,13 @@ class ShardedApproxCounter:
         self.counter = ApproxCounter(self.device)
         self.counter.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._counts = None
+        # the ranks' contexts form one NCCL communicator through the C ABI; rank 0 creates the id
+        self.abi_comm = False
+        if self.world > 1 and dist.get_backend(group) == "nccl":
+            box = [ApproxCounter.comm_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            self.counter.comm_init_rank(self.world, self.rank, box[0])
+            self.abi_comm = True
 
     def close(self):
         self.counter.close()
@@ -71,8 +80,11 @@ class ShardedApproxCounter:
         """Asynchronous on the torch current stream; returns the device tensor."""
         self.counter.set_stream(self.torch.cuda.current_stream(self.device).cuda_stream)
         if self._counts.numel():
-            self.counter.scan(self._counts.data_ptr())
-            allreduce_counts(self._counts, self.group)
+            if self.abi_comm:
+                self.counter.scan_allreduce(self._counts.data_ptr())
+            else:
+                self.counter.scan(self._counts.data_ptr())
+                allreduce_counts(self._counts, self.group)
         return self._counts
 
     def errorCount(self, kmers, k):

@@ -2,7 +2,7 @@
 """bench.py — approximate-count throughput of the B200 path (and of the CPU
 reference arm) on BASELINE.json's synthetic workloads.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3] [--scaling strong|weak] [--impl b200|reference]
 
 A *step* is one pass of the hot path (errorCount, reference :531-601) over one
 batch: all `lim` query k-mers against the sampled read STARTS (n x sl bases) and
@@ -10,9 +10,14 @@ the sampled read ENDS (n x (sl+1) bases, :463) — what the reference does once
 per run.  Metric: GCUPS = k x Q x (sum of sampled read lengths) / t / 1e9
 (SURVEY.md §8d); `queries_per_s` = 2Q / t rides along.
 
-N > 1 (torchrun, one rank per GPU): weak scaling — every rank holds its own
-n-read shard of the synthetic read stream, scans it for all queries and the
-per-k-mer count vectors are summed with one small NCCL all-reduce per end.
+Default workload: BASELINE config 3 (1M reads, k=20, sl=150, lim=5000 — the
+configuration BASELINE.json assigns to 2/4/8 GPUs; it fits one GPU and a step
+is tens of milliseconds, so the timed region is about a second).  N > 1
+(torchrun, one rank per GPU): STRONG scaling by default — the one n-read job is
+split over the ranks in contiguous blocks of reads, every rank scans its shard
+for all queries and the count vectors of both ends are summed with ONE small
+NCCL all-reduce per step, issued through the C ABI (apc_allreduce_counts).
+The C2 weak-scaling number of round 1 rides along as `c2_weak_value`.
 
 One JSON line on stdout (rank 0).  See DESIGN.md §Measurement for every key.
 """
@@ -151,23 +156,20 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def make_ends(w, first, pinned_torch=None, count=None):
-    """Sampled starts and ends of synthetic reads [first, first+n): uint8[n, sl], uint8[n, sl+1]."""
-    from approx_counter_b200 import host
-    n, sl = (w["n"] if count is None else count), w["sl"]
-    if pinned_torch is not None:
-        torch = pinned_torch
-        t0 = torch.empty((n, sl), dtype=torch.uint8, pin_memory=True)
-        t1 = torch.empty((n, sl + 1), dtype=torch.uint8, pin_memory=True)
-        a, b = t0.numpy(), t1.numpy()
-        host.synth_ends(w["seed"], first, n, sl, False, a)
-        host.synth_ends(w["seed"], first, n, sl, True, b)
-        return (a, b), (t0, t1)
-    return (host.synth_ends(w["seed"], first, n, sl, False), host.synth_ends(w["seed"], first, n, sl, True)), None
+def host_threads():
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: size teams from the CPUs this process may run on
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
-def columns_per_step(w, q_start, q_end):
-    return q_start * w["n"] * w["sl"] + q_end * w["n"] * (w["sl"] + 1)
+def make_config(w, scaling, world):
+    """The `config` object — the SAME keys and values in both arms (the driver compares them)."""
+    return {"workload": w["text"] + ", both ends (start n x sl, end n x (sl+1))", "k": w["k"],
+            "reads_total": w["n"] * (world if scaling == "weak" else 1), "sl": w["sl"], "lim": w["lim"],
+            "seed": w["seed"], "scaling": scaling,
+            "l2": f"GPU arm: flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset outside the event pairs)"}
 
 
 CPU_NOTES = {
@@ -202,21 +204,17 @@ def cpu_leg(w, ends, queries, target_s, threads=0, algo="fm"):
     algo "fm": FM index build + search-scheme search, what the reference's errorCount does; "scan": the
     Myers bit-vector scan with the reference's `omp for schedule(dynamic)` over k-mers (:567)."""
     k = w["k"]
-    # torchrun exports OMP_NUM_THREADS=1 to every rank: size the team from the CPUs this
-    # process may run on, not from the OpenMP default
+    n_have = ends[0].shape[0]
     if threads <= 0:
-        try:
-            threads = len(os.sched_getaffinity(0))
-        except AttributeError:
-            threads = os.cpu_count() or 1
-    cpu_run(algo, ends, queries, k, min(w["n"], 64), threads)  # library load, OpenMP team start
-    r = min(w["n"], 2048 if algo == "fm" else 64)
+        threads = host_threads()
+    cpu_run(algo, ends, queries, k, min(n_have, 64), threads)  # library load, OpenMP team start
+    r = min(n_have, 2048 if algo == "fm" else 64)
     t, cols, build, search = cpu_run(algo, ends, queries, k, r, threads)  # calibration: grow until the run is long enough to trust
-    while t < 0.3 and r < w["n"]:
-        r = min(w["n"], r * 4)
+    while t < 0.3 and r < n_have:
+        r = min(n_have, r * 4)
         t, cols, build, search = cpu_run(algo, ends, queries, k, r, threads)
     for _ in range(3):  # extrapolate to the target, and again if the first guess came out short (first calls are slow)
-        r2 = int(max(32, min(w["n"], target_s * r / max(t, 1e-6))))
+        r2 = int(max(32, min(n_have, target_s * r / max(t, 1e-6))))
         if r2 == r or (r2 < r and t < 2 * target_s):
             break
         r = r2
@@ -224,36 +222,41 @@ def cpu_leg(w, ends, queries, target_s, threads=0, algo="fm"):
         if t > 0.6 * target_s:
             break
     return {"seconds": t, "columns": cols, "reads": r, "threads": threads, "algo": algo,
-            "gcups": k * cols / t / 1e9, "index_build_s": build, "search_s": search,
-            "queries_per_s": (len(queries[0]) + len(queries[1])) / t * (r / w["n"])}
+            "gcups": k * cols / t / 1e9, "index_build_s": build, "search_s": search}
 
 
 def reference_queries(w, ends):
-    """Top-`lim` exact k-mers of each end with the CPU restatement (:874, :898) — set-up of the
-    reference arm only (the B200 arm uses its own exact stage on the GPU)."""
+    """Top-`lim` exact k-mers of each end with the CPU restatement (:874, :898; all host threads for the count,
+    threshold-cut top-N — both held equal to the plain restatement in tests/test_oracle.py).  Set-up of the
+    reference arm only: the B200 arm gets its queries from its own exact stage on the GPU."""
     from oracle import orc
     thr = orc.adjust_threshold(PARAM_LC, 16, w["k"])
     out = []
     for sample in ends:
         codes, offs = orc.encode_matrix(sample)
-        keys, cnts, _ = orc.count_kmers(codes, offs, w["k"], thr)
-        km, _ = orc.get_most_frequent(keys, cnts, w["lim"], w["k"])
+        keys, cnts, _ = orc.count_kmers_mt(codes, offs, w["k"], thr)
+        km, _ = orc.get_most_frequent_fast(keys, cnts, w["lim"], w["k"])
         out.append(km)
     return out
 
 
 def run_reference(args, w):
+    """The reference arm: the CPU path on the box's host cores, everything from oracle/ (the product library is
+    never loaded in this process)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import __graft_entry__ as g
     g.build_oracle()
+    from oracle import orc
+    world = max(1, args.gpus)
+    n_total = w["n"] * (world if args.scaling == "weak" else 1)
     t_gen = time.perf_counter()
-    ends, _ = make_ends(w, 0)
+    ends = (orc.synth_ends(w["seed"], 0, w["n"], w["sl"], False), orc.synth_ends(w["seed"], 0, w["n"], w["sl"], True))
     queries = reference_queries(w, ends)
     log(f"[reference] workload + queries ready in {time.perf_counter() - t_gen:.1f}s")
     # bounded sample per step so that warmup+steps stay within a few minutes
-    per_step = max(0.5, min(3.0, 150.0 / max(1, args.steps + args.warmup)))
+    per_step = max(0.5, min(3.0, 120.0 / max(1, args.steps + args.warmup)))
     first = cpu_leg(w, ends, queries, per_step, algo="fm")
     r = first["reads"]
     k = w["k"]
@@ -272,17 +275,16 @@ def run_reference(args, w):
     total = sum(times)
     cols = len(queries[0]) * r * ends[0].shape[1] + len(queries[1]) * r * ends[1].shape[1]
     value = k * cols * args.steps / total / 1e9
-    sample = (f"first {r} of {w['n']} sampled reads of both ends x all {len(queries[0])}+{len(queries[1])} "
+    sample = (f"first {r} of {n_total} sampled reads of both ends x all {len(queries[0])}+{len(queries[1])} "
               f"query k-mers per step ({cols:.3g} columns/step; index build {sum(builds) / args.steps:.2f} s + "
               f"search {sum(searches) / args.steps:.2f} s per step)")
     line = {
         "impl": "reference", "metric": "approx_count_gcups", "value": value, "unit": "GCUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": w["text"] + ", both ends", "k": k, "reads": w["n"], "sl": w["sl"], "lim": w["lim"],
-                   "seed": w["seed"]},
-        "queries_per_s": (len(queries[0]) + len(queries[1])) * args.steps / total * (r / w["n"]),
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": make_config(w, args.scaling, world),
+        "queries_per_s": (len(queries[0]) + len(queries[1])) * args.steps / total * (r / n_total),
         "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": first["threads"], "kind": "port",
                          "sample": sample, "algo": "fm-index",
                          "index_build_s_per_step": sum(builds) / args.steps,
@@ -297,9 +299,222 @@ def run_reference(args, w):
 
 
 # ------------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed as plumbing: barrier, max over ranks, broadcast of small host arrays."""
+
+    def __init__(self, torch, dev, world):
+        self.torch, self.dev, self.world = torch, dev, world
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=dev)
+            self.dist = dist
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def bcast_u64(self, arr, cap):
+        """Broadcast a uint64 host array of at most `cap` entries from rank 0."""
+        torch = self.torch
+        t = torch.zeros(cap + 1, dtype=torch.int64, device=self.dev)
+        if arr is not None:
+            t[0] = len(arr)
+            t[1: 1 + len(arr)] = torch.from_numpy(np.ascontiguousarray(arr).view(np.int64)).to(self.dev)
+        if self.dist:
+            self.dist.broadcast(t, 0)
+        h = t.cpu().numpy()
+        return h[1: 1 + int(h[0])].view(np.uint64).copy()
+
+    def bcast_bytes(self, b, n):
+        torch = self.torch
+        t = torch.zeros(n, dtype=torch.uint8, device=self.dev)
+        if b is not None:
+            t.copy_(torch.frombuffer(bytearray(b), dtype=torch.uint8))
+        if self.dist:
+            self.dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+class Job:
+    """One workload resident on this rank's GPU: the rank's shard of both sampled ends, the query k-mers of both
+    ends, ONE device vector for the counts of both ends (so that the ranks' vectors are summed with a single
+    all-reduce per step) — everything through the C ABI (ApproxCounter = ctypes over include/apc.h)."""
+
+    def __init__(self, torch, dev, local_rank, stream, w, first, n, pinned=True, seed=None):
+        from approx_counter_b200 import ApproxCounter, host
+        self.torch, self.dev, self.w, self.n, self.first, self.stream = torch, dev, w, n, first, stream
+        sl = w["sl"]
+        seed = w["seed"] if seed is None else seed
+        self.pinned = [torch.empty((n, sl + b), dtype=torch.uint8, pin_memory=pinned) for b in (0, 1)]
+        self.ends = [t.numpy() for t in self.pinned]
+        for b, a in enumerate(self.ends):
+            host.synth_ends(seed, first, n, sl, bool(b), a)
+        self.ctxs = [ApproxCounter(local_rank), ApproxCounter(local_rank)]
+        for c, s in zip(self.ctxs, self.ends):
+            c.set_stream(stream.cuda_stream)
+            c.upload_sample_ptr(s.ctypes.data, s.shape[0], s.shape[1])
+        self.queries = None
+
+    def exact_queries(self, lim):
+        """Top-`lim` exact k-mers of each end from the GPU exact stage over what this job holds."""
+        from approx_counter_b200 import host
+        thr = host.adjust_threshold(PARAM_LC, 16, self.w["k"])
+        out, ms = [], []
+        for c in self.ctxs:
+            km, _, _, _ = c.count_kmers_topn(self.w["k"], thr, lim)
+            ms.append(c.timing()["exact_ms"])
+            out.append(km)
+        return out, ms
+
+    def set_queries(self, queries, options=()):
+        torch = self.torch
+        self.queries = queries
+        self.q = [len(q) for q in queries]
+        self.counts = torch.zeros(sum(self.q), dtype=torch.int64, device=self.dev)
+        self.ptrs = [self.counts.data_ptr(), self.counts.data_ptr() + 8 * self.q[0]]
+        for c, q in zip(self.ctxs, queries):
+            for name, value in options:
+                c.set_option(name, value)
+            c.set_queries(q, self.w["k"])
+
+    def step(self, kernel_events=None):
+        """Scan both ends into the shared count vector, then one all-reduce over the ranks (a no-op on one GPU)."""
+        torch = self.torch
+        launches = 0
+        if kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+        for c, p in zip(self.ctxs, self.ptrs):
+            c.scan(p)
+            launches += c.timing_launches()
+        if kernel_events is not None:
+            e1.record(self.stream)
+            kernel_events.append((e0, e1))
+        self.ctxs[0].allreduce_counts(self.ptrs[0], sum(self.q))
+        return launches
+
+    def columns(self, n_reads=None):
+        n = self.n if n_reads is None else n_reads
+        sl = self.w["sl"]
+        return self.q[0] * n * sl + self.q[1] * n * (sl + 1)
+
+    def stats(self):
+        a, b = (c.scan_stats() for c in self.ctxs)
+        return {k: a[k] + b[k] for k in a}
+
+    def host_counts(self):
+        return self.counts.cpu().numpy().view(np.uint64).copy()
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+
+
+def timed_steps(torch, job, dist, flush, steps, warmup, sampler_factory=None):
+    """W untimed + K timed steps, CUDA events on the launching stream around every step (the L2 flush between steps
+    sits outside the event pairs), barrier + synchronize on both sides.  Returns device ms (max over ranks),
+    kernel ms (scan launches only), launches, wall marks, clocks."""
+    stream = job.stream
+    for _ in range(max(warmup, 0)):
+        flush.zero_()
+        job.step()
+    dist.barrier()
+    job.stats()  # reset the executed-row tally: only the timed steps count
+    sampler = sampler_factory() if sampler_factory else None
+    if sampler_factory:
+        time.sleep(0.12)  # let the sampler produce its first rows; every rank waits alike
+    dist.barrier()
+    launches = 0
+    step_events, kernel_events = [], []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        launches += job.step(kernel_events)
+        e1.record(stream)
+        step_events.append((e0, e1))
+    dist.barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1) if sampler is not None else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in step_events)
+    kern_ms = sum(a.elapsed_time(b) for a, b in kernel_events)
+    dev_ms, kern_ms = dist.max(dev_ms, kern_ms)
+    return {"dev_ms": dev_ms, "kern_ms": kern_ms, "launches": launches, "t0": t0, "t1": t1, "clocks": clocks,
+            "stats": job.stats()}
+
+
+def run_e2e(torch, dev, job, dist, steps):
+    """The same metric end to end through the C ABI with HOST buffers: per step and per end the H2D copy of the
+    sampled reads (pinned) and of the k-mers, query planning, scan; one all-reduce; D2H of the counts.  The two
+    ends run on two streams (the upload of one overlaps the scan of the other) and consecutive steps are
+    pipelined two deep with alternating output buffers, as a host loop over batches would do; wall clock around
+    the whole loop, every step's counts checked afterwards."""
+    k = job.w["k"]
+    world = dist.world
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+    h_q = [torch.from_numpy(q.view(np.int64)).pin_memory() for q in job.queries]
+    nq = sum(job.q)
+    h_out = [torch.zeros(nq, dtype=torch.int64).pin_memory() for _ in range(2)]
+    d_out = [torch.zeros(nq, dtype=torch.int64, device=dev) for _ in range(2)]
+    done = [None, None]
+    for c, es in zip(job.ctxs, streams):
+        c.set_stream(es.cuda_stream)
+
+    def enqueue(i):
+        slot = i & 1
+        if done[slot] is not None:
+            done[slot].synchronize()  # the output buffers of step i-2 are free again
+        base = d_out[slot].data_ptr()
+        for e, (c, es, s, q) in enumerate(zip(job.ctxs, streams, job.ends, h_q)):
+            with torch.cuda.stream(es):
+                c.upload_sample_ptr_async(s.ctypes.data, s.shape[0], s.shape[1])
+                c.set_queries_ptr(q.data_ptr(), q.numel(), k)
+                c.scan(base + (8 * job.q[0] if e else 0))
+        ev = torch.cuda.Event()
+        ev.record(streams[1])
+        streams[0].wait_event(ev)
+        with torch.cuda.stream(streams[0]):
+            job.ctxs[0].allreduce_counts(base, nq)
+            h_out[slot].copy_(d_out[slot], non_blocking=True)
+        done[slot] = torch.cuda.Event()
+        done[slot].record(streams[0])
+        # end 1 of the NEXT step must not overwrite its count half before this step's all-reduce has read it
+        streams[1].wait_event(done[slot])
+
+    for i in range(3):
+        enqueue(i)
+    torch.cuda.synchronize(dev)
+    done[0] = done[1] = None
+    dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        enqueue(i)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    e2e_s = dist.max(time.perf_counter() - t0)[0]
+    for c in job.ctxs:
+        c.set_stream(job.stream.cuda_stream)
+    h2d = int(job.ends[0].nbytes + job.ends[1].nbytes + 8 * nq)
+    outs = [h.numpy().view(np.uint64).copy() for h in h_out]
+    return e2e_s, h2d, int(8 * nq), outs
+
+
 def run_b200(args, w):
     import torch
-    import torch.distributed as dist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -312,247 +527,178 @@ def run_b200(args, w):
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    dist = Dist(torch, dev, world)
 
-    from approx_counter_b200 import ApproxCounter, host, allreduce_counts, load
+    from approx_counter_b200 import ApproxCounter, host, load, shard_bounds
     load()  # fails loudly if libapc.so is missing
-    k, n, sl, lim = w["k"], w["n"], w["sl"], w["lim"]
+    k, sl, lim = w["k"], w["sl"], w["lim"]
     stream = torch.cuda.Stream(dev)  # everything below runs on this (non-default) stream
     torch.cuda.set_stream(stream)
-
-    # ---- inputs: this rank's shard of the synthetic read stream, in pinned host memory
-    if args.scaling == "strong":
-        # one job of n reads split over the ranks (contiguous blocks of 32-read tiles)
-        from approx_counter_b200 import shard_bounds
-        lo, hi = shard_bounds(n, rank, world)
-        n_total, first, n = n, lo, hi - lo
-    else:
-        n_total, first = n * world, rank * n
-    (h_start, h_end), pinned = make_ends(w, first, pinned_torch=torch, count=n)
-    ends = (h_start, h_end)
-    ctxs = [ApproxCounter(local_rank), ApproxCounter(local_rank)]
-    for c, s in zip(ctxs, ends):
-        c.set_option("scan_variant", args.scan_variant)
-        c.set_stream(stream.cuda_stream)
-        c.upload_sample_ptr(s.ctypes.data, s.shape[0], s.shape[1])
-
-    # ---- queries: top-`lim` exact k-mers per end from the GPU exact stage (rank 0's shard,
-    # broadcast so that every rank scans for the same k-mers)
-    thr = host.adjust_threshold(PARAM_LC, 16, k)
-    queries, exact_ms = [], []
-    for c in ctxs:
-        km, ct, nd, hn = c.count_kmers_topn(k, thr, lim)
-        exact_ms.append(c.timing()["exact_ms"])
-        t = torch.zeros(lim, dtype=torch.int64, device=dev)
-        cnt = torch.tensor([len(km)], dtype=torch.int64, device=dev)
-        t[: len(km)] = torch.from_numpy(km.view(np.int64)).to(dev)
-        if world > 1:
-            dist.broadcast(t, 0)
-            dist.broadcast(cnt, 0)
-        queries.append(t[: int(cnt.item())].cpu().numpy().view(np.uint64).copy())
-    q_start, q_end = len(queries[0]), len(queries[1])
-    if min(q_start, q_end) == 0:
-        raise SystemExit("bench.py: the exact stage returned no query k-mers")
-    counts = [torch.zeros(len(q), dtype=torch.int64, device=dev) for q in queries]
-    for c, q in zip(ctxs, queries):
-        if args.plan_alive_pct >= 0:
-            c.set_option("plan_alive_pct", args.plan_alive_pct)
-        if args.sg_per_job > 0:
-            c.set_option("tiles_per_job", args.sg_per_job)
-        c.set_queries(q, k)
-
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    launches = [0]
-    kernel_events = []
+    options = [("scan_variant", args.scan_variant)]
+    if args.plan_alive_pct >= 0:
+        options.append(("plan_alive_pct", args.plan_alive_pct))
+    if args.sg_per_job > 0:
+        options.append(("tiles_per_job", args.sg_per_job))
+    if args.no_graph:
+        options.append(("scan_graph", 0))
 
-    def step(record=False):
-        for c, out in zip(ctxs, counts):
-            if record:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-            c.scan(out.data_ptr())
-            if record:
-                e1.record(stream)
-                kernel_events.append((e0, e1))
-            launches[0] += c.timing_launches()
-            allreduce_counts(out)
+    # ---- this rank's shard of the synthetic read stream, in pinned host memory
+    if args.scaling == "strong":  # one job of n reads split over the ranks (contiguous blocks of 32-read tiles)
+        n_total = w["n"]
+        lo, hi = shard_bounds(n_total, rank, world)
+        first, n = lo, hi - lo
+    else:                         # every rank holds its own n-read shard of the stream
+        n_total, first, n = w["n"] * world, rank * w["n"], w["n"]
+    job = Job(torch, dev, local_rank, stream, w, first, n)
 
-    def barrier():
-        torch.cuda.synchronize(dev)
+    # ---- the ranks form one NCCL communicator through the C ABI (apc_comm_*): rank 0 creates the id
+    if world > 1:
+        uid = dist.bcast_bytes(ApproxCounter.comm_unique_id() if rank == 0 else None, 128)
+        job.ctxs[0].comm_init_rank(world, rank, uid)
+
+    # ---- queries: the top-`lim` exact k-mers per end of the WHOLE job's sample from the GPU exact stage (rank 0;
+    # broadcast so that every rank scans for the same k-mers).  With the sample sharded, rank 0 loads the whole
+    # sample once for this set-up step.
+    exact_ms = None
+    qs = [None, None]
+    if rank == 0:
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+            whole = Job(torch, dev, local_rank, stream, w, 0, n_total, pinned=False)
+            qs, exact_ms = whole.exact_queries(lim)
+            whole.close()
+            del whole
+        else:
+            qs, exact_ms = job.exact_queries(lim)
+            qs2, exact_ms2 = job.exact_queries(lim)  # second call: scratch allocated, kernels loaded
+            exact_ms = {"first_call": exact_ms, "steady": exact_ms2}
+    queries = [dist.bcast_u64(q, lim) for q in qs]
+    if min(len(q) for q in queries) == 0:
+        raise SystemExit("bench.py: the exact stage returned no query k-mers")
+    job.set_queries(queries, options)
+    q_start, q_end = job.q
 
-    for _ in range(max(args.warmup, 0)):
-        flush.zero_()
-        step()
-    barrier()
-
-    # ---- timed region: K steps, device events around every step (the L2 flush between
-    # steps sits outside the event pairs), clocks sampled meanwhile
+    # ---- timed region
     gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
-    sampler = ClockSampler(gpu_uuid if gpu_uuid.startswith("GPU-") else "GPU-" + gpu_uuid) if rank == 0 else None
-    time.sleep(0.12)  # let the sampler produce its first rows; every rank waits alike
-    barrier()         # ... and all ranks enter the timed region together
-    launches[0] = 0
-    step_events = []
-    t_mark0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        step(record=True)
-        e1.record(stream)
-        step_events.append((e0, e1))
-    barrier()
-    t_mark1 = time.perf_counter()
-    clocks = sampler.stop(t_mark0, t_mark1) if sampler is not None else None
-    if os.environ.get("APC_BS_STATS"):  # A/B library built with -DAPC_BS_STATS (tools/build_ab.sh)
-        log("[bs_stats] share of tests after which the deep rows were computed:",
-            [round(c.microbench("bs_stats"), 4) for c in ctxs])
-    dev_ms = sum(a.elapsed_time(b) for a, b in step_events)
-    kern_ms = sum(a.elapsed_time(b) for a, b in kernel_events)
-    n_launch = launches[0]
-    t = torch.tensor([dev_ms, kern_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, kern_ms = float(t[0]), float(t[1])
-
-    cols_rank = q_start * n * sl + q_end * n * (sl + 1)
-    cols_job = q_start * n_total * sl + q_end * n_total * (sl + 1)
+    factory = (lambda: ClockSampler(gpu_uuid if gpu_uuid.startswith("GPU-") else "GPU-" + gpu_uuid)) if rank == 0 else None
+    res = timed_steps(torch, job, dist, flush, args.steps, args.warmup, factory)
+    dev_ms, kern_ms = res["dev_ms"], res["kern_ms"]
+    cols_rank, cols_job = job.columns(), job.columns(n_total)
     value = k * cols_job * args.steps / (dev_ms / 1e3) / 1e9
-    final_counts = [c.cpu().numpy().view(np.uint64).copy() for c in counts]
+    final_counts = job.host_counts()
 
-    # ---- end to end through the C ABI with HOST buffers: per step, per end, H2D of the
-    # sampled reads + k-mers, scan, (all-reduce), D2H of the counts
-    e2e_steps = max(1, min(args.steps, 20))
-    h_q = [torch.from_numpy(q.view(np.int64)).pin_memory() for q in queries]
-    h_out = [torch.zeros(len(q), dtype=torch.int64).pin_memory() for q in queries]
-
-    # each end gets its own stream so that the upload of one sample overlaps the scan of the other
-    e2e_streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-    for c, es in zip(ctxs, e2e_streams):
-        c.set_stream(es.cuda_stream)
-
-    def e2e_step():
-        for c, es, s, q, o, d in zip(ctxs, e2e_streams, ends, h_q, h_out, counts):
-            with torch.cuda.stream(es):
-                c.upload_sample_ptr_async(s.ctypes.data, s.shape[0], s.shape[1])
-                if world == 1:
-                    c.errorCount_ptr_async(q.data_ptr(), q.numel(), k, o.data_ptr())
-                else:
-                    c.set_queries_ptr(q.data_ptr(), q.numel(), k)
-                    c.scan(d.data_ptr())
-                    allreduce_counts(d)
-                    o.copy_(d, non_blocking=True)
-        torch.cuda.synchronize(dev)
-
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    # ---- parity self-check of the multi-GPU result: rank 0 rescans the union of all shards on ITS GPU alone
+    parity = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t[0])
+        if rank == 0:
+            tot = np.zeros(q_start + q_end, np.uint64)
+            chunk = max(1, min(n_total, 1 << 20))
+            for lo in range(0, n_total, chunk):
+                u = Job(torch, dev, local_rank, stream, w, lo, min(chunk, n_total - lo), pinned=False)
+                u.set_queries(queries, options)
+                u.step()
+                torch.cuda.synchronize(dev)
+                tot += u.host_counts()
+                u.close()
+                del u
+            if not np.array_equal(tot, final_counts):
+                raise SystemExit("bench.py: PARITY FAILURE — the all-reduced counts of the sharded scan differ from a "
+                                 "single-GPU scan of the same reads")
+            parity = f"ok: all-reduced counts of {world} shards == single-GPU scan of all {n_total} reads ({q_start}+{q_end} k-mers)"
+
+    # ---- end to end through the C ABI with host buffers
+    e2e_steps = max(2, min(args.steps, 20))
+    e2e_s, h2d, d2h, outs = run_e2e(torch, dev, job, dist, e2e_steps)
     e2e_value = k * cols_job * e2e_steps / e2e_s / 1e9
-    for o, f in zip(h_out, final_counts):
-        if not np.array_equal(o.numpy().view(np.uint64), f):
+    for o in outs:
+        if not np.array_equal(o, final_counts):
             raise SystemExit("bench.py: end-to-end counts differ from the resident-path counts")
-    h2d = int(h_start.nbytes + h_end.nbytes + 8 * (q_start + q_end))
-    d2h = int(8 * (q_start + q_end))
+
+    # ---- continuity with round 1: C2, weak scaling (every rank its own 100k-read shard), device-timed only
+    c2 = None
+    if args.workload != "C2" and not args.no_extras:
+        w2 = dict(WORKLOADS["C2"])
+        j2 = Job(torch, dev, local_rank, stream, w2, rank * w2["n"], w2["n"])
+        if world > 1:
+            j2.ctxs[0].comm_init_rank(world, rank, dist.bcast_bytes(ApproxCounter.comm_unique_id() if rank == 0 else None, 128))
+        q2 = j2.exact_queries(w2["lim"])[0] if rank == 0 else [None, None]
+        j2.set_queries([dist.bcast_u64(q, w2["lim"]) for q in q2], options)
+        r2 = timed_steps(torch, j2, dist, flush, 20, 5)
+        c2 = {"value": w2["k"] * j2.columns(w2["n"] * world) * 20 / (r2["dev_ms"] / 1e3) / 1e9, "unit": "GCUPS",
+              "ms_per_step": r2["dev_ms"] / 20, "scaling": "weak", "reads_per_gpu": w2["n"],
+              "workload": w2["text"]}
+        j2.close()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        job.close()
+        dist.close()
         return 0
 
-    # ---- roofline of the dominant kernel (approx_scan_kernel)
+    # ---- roofline of the dominant kernels: the integer ALU pipe (LOP3), measured both ways
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    int_peak = ctxs[0].measure_int_peak()
+    clocks = res["clocks"]
+    int_peak = job.ctxs[0].measure_int_peak()
+    lop3_peak = int_peak["lop3_ops_per_s"]  # lane-ops/s of a dependent-free LOP3 stream on every SM (peak_kernels.cu)
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
     sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    alu_peak = sms * 4 * 16 * sm_max * 1e6  # ALU pipe: 16 lanes/clk/SMSP (B300_MICROARCH.md:85)
-    # a scan is up to three launches (k-mer quads, pairs, then the ungrouped k-mers): the roofline unit is the scan
-    n_scans = max(len(kernel_events), 1)
-    per_launch_s = kern_ms / 1e3 / n_scans
-    cols_launch = cols_rank / 2.0
-    # no kernel can retire more than one instruction per SMSP per clock, and even four k-mers sharing 3k/4 of
-    # their rows cost 5 * 7k/16 / 32 > 0.5 lane-operations per column; a faster reading means the event pairs
-    # did not contain the kernel (e.g. it ran on another stream)
+    alu_nominal = sms * 4 * 16 * sm_max * 1e6  # ALU pipe: 16 lanes/clk/SMSP (B300_MICROARCH.md:85)
+    kern_s = kern_ms / 1e3
+    st = res["stats"]  # LOP3 warp instructions of the timed steps on THIS rank (x 32 = lane operations)
+    if st["scans"] != 2 * args.steps:
+        raise SystemExit(f"bench.py: {st['scans']} scans tallied in the timed region, expected {2 * args.steps}")
+    executed = 32.0 * st["lop3_executed"] / kern_s
+    planned = 32.0 * st["lop3_planned"] / kern_s
+    algorithmic = ALGO_OPS_PER_COLUMN * cols_rank * args.steps / kern_s
     issue_peak = sms * 4 * 32 * sm_max * 1e6
-    if 0.5 * cols_launch / per_launch_s > issue_peak:
-        raise SystemExit("bench.py: implausible kernel time — the timed region did not contain the scan kernel")
-    achieved = ALGO_OPS_PER_COLUMN * cols_launch / per_launch_s
-    traffic = ncu_alu = None
-    try:  # figures from the committed ncu capture of this kernel on this workload (profiles/)
+    if executed > issue_peak:
+        raise SystemExit("bench.py: implausible kernel time — the timed region did not contain the scan kernels")
+    n_scans = 2 * args.steps
+    traffic = profiled = None
+    try:  # figures from the committed ncu captures (profiles/): not measured in this run
         prof = json.load(open(os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")))
         traffic = prof.get(args.workload, {}).get("dram_bytes_per_launch")
-        ncu_alu = prof.get(args.workload, {}).get("alu_pipe_pct")
+        profiled = prof.get(args.workload, {})
     except Exception:
         pass
-    # bit planes: one uint4 per (32-read group, column), columns padded to 16, groups to 32 per super-group;
-    # + the k-mers and the counts
     cols_padded = ((sl + 1 + 15) // 16) * 16
-    hbm_bytes_launch = ((n + 1023) // 1024) * 32 * cols_padded * 16 + 16 * q_start
-    # What the scan plan costs on the ALU pipe: it groups k-mers into units whose shared rows are computed once;
-    # a row of a unit costs 5 LOP3 per column and 1024 reads (32 lanes x 32 reads; bitslice_core.cuh).  Dead-row
-    # skipping then leaves out the deep rows of a unit in the columns where nothing can reach them, which is
-    # data dependent: `planned` is the instruction count WITHOUT skipping (an upper bound of what is executed),
-    # the executed share is read from ncu (sm__inst_executed_pipe_alu, profiles/).
-    from approx_counter_b200 import plan_queries
-    plan_rows, plan_units, plan_reversed = [], [], []
-    for q in queries:
-        pl = plan_queries(q, k)
-        rows = sum(int(u) * (k - int(t) + int(g) * int(t)) for u, t, g in zip(pl["units"], pl["shape_t"], pl["shape_g"]))
-        rows += (len(q) - int((pl["units"] * pl["shape_g"]).sum())) * k
-        plan_rows.append(rows)
-        plan_units.append([int(u) for u in pl["units"]])
-        plan_reversed.append(int(pl["reversed"].sum()))
-    n_sg_rank = (n + 1023) // 1024
-    lop3_lane_ops = sum(5.0 * 32 * rows * n_sg_rank * (2 * ((L + 1) // 2)) for rows, L in zip(plan_rows, (sl, sl + 1)))
-    planned = lop3_lane_ops / (kern_ms / 1e3 / max(args.steps, 1))
+    hbm_bytes_scan = ((n + 1023) // 1024) * 32 * cols_padded * 16 + 16 * q_start
     roofline = {
-        "bound": "int-alu", "kernel": "bs_group_kernel<K,P,G> (one launch per unit shape in use) + bs_scan_kernel<K> (ungrouped k-mers); "
-                                      "one scan = up to 13 concurrent launches", "achieved": achieved / 1e12, "peak": alu_peak / 1e12,
-        "unit": "Tint-op/s", "frac": achieved / alu_peak, "traffic": traffic, "ncu_alu_pipe_pct": ncu_alu,
-        "peak_source": f"ALU pipe nominal = {sms} SM x 4 SMSP x 16 lanes/clk x {sm_max:.0f} MHz (SURVEY.md §8d)",
-        "algorithmic_ops_per_column": ALGO_OPS_PER_COLUMN, "columns_per_launch": cols_launch,
-        "avg_launch_ms": per_launch_s * 1e3, "scans_timed": n_scans, "launches_timed": n_launch,
+        "bound": "int-alu",
+        "kernel": "bs_group_kernel<K,P,G> (one launch per unit shape in use) + bs_scan_kernel<K> (ungrouped k-mers); one scan "
+                  "= up to 13 concurrent launches, replayed as one CUDA graph",
+        "achieved": executed / 1e12, "peak": lop3_peak / 1e12, "unit": "T lane-op/s", "frac": executed / lop3_peak,
+        "what": "EXECUTED LOP3 lane-operations of the timed scans (5 per automaton row, text column and 32 reads; the rows "
+                "skipped by dead-row skipping are tallied by the kernels at run time and NOT counted) / kernel time, against "
+                "the LOP3 peak measured in this run on this GPU (apc_measure_int_peak)",
+        "frac_of_nominal_alu_peak": executed / alu_nominal,
+        "frac_planned": planned / lop3_peak,
+        "frac_algorithmic": algorithmic / lop3_peak,
+        "algorithmic_note": "SURVEY.md §8d counts 16 int ops per (k-mer, text position) column (Myers/Hyyro); bit-slicing, "
+                            "row sharing between k-mers and dead-row skipping do far fewer, so this figure exceeds 1",
+        "peak_source": "measured: dependent-free LOP3 stream on all SMs, this run; nominal ALU pipe = "
+                       f"{sms} SM x 4 SMSP x 16 lanes/clk x {sm_max:.0f} MHz = {alu_nominal / 1e12:.2f} T lane-op/s",
+        "traffic": traffic,
         "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
-        "planned": {"lop3_Tlane_ops_per_s": planned / 1e12, "frac_of_alu_peak": planned / alu_peak,
-                    "rows_per_scan": plan_rows, "rows_if_one_kmer_per_warp": [len(q) * k for q in queries],
-                    "units_per_shape": plan_units, "kmers_scanned_backwards": plan_reversed,
-                    "note": "LOP3 of the scan plan if every unit row were computed in every column (5 per row, column "
-                            "and 1024 reads) / time, against the ALU peak; above 1 = what dead-row skipping saves. "
-                            "`frac` is against the ALGORITHMIC 16 ops per column; the executed utilisation is "
-                            "ncu_alu_pipe_pct"},
-        "measured_int_peaks_Tops": {kk: v / 1e12 for kk, v in int_peak.items()},
-        "frac_of_measured_lop3_peak": achieved / int_peak["lop3_ops_per_s"],
-        "hbm": {"algorithmic_bytes_per_launch": hbm_bytes_launch,
-                "achieved_gbs": hbm_bytes_launch / per_launch_s / 1e9,
-                "peak_gbs": peaks.get("hbm_gbs"), "note": "the text (bit planes, 0.5 B per base) is re-read from L2 "
-                "by every k-mer; the kernel is bound by the ALU pipe (LOP3), HBM is idle"},
+        "avg_scan_ms": kern_ms / n_scans, "scans_timed": n_scans, "launches_timed": res["launches"],
         "sm_mhz_during_run": sm_mhz,
+        "hbm": {"algorithmic_bytes_per_scan": hbm_bytes_scan, "achieved_gbs": hbm_bytes_scan / (kern_s / n_scans) / 1e9,
+                "peak_gbs": peaks.get("hbm_gbs"), "note": "the text (bit planes, 0.5 B per base) is re-read from L2 by every "
+                "unit; the kernels are bound by the ALU pipe (LOP3), HBM is idle"},
+        "ncu_profiled": profiled,
     }
 
-    # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
-    cpu = None
+    # ---- N = 1 only: CPU baseline on a bounded sample + oracle spot check, the floor, the wide-offset stream
+    cpu = floor = wide = None
     if world == 1 and not args.no_cpu_baseline:
         import __graft_entry__ as g
         g.build_oracle()
-        leg = cpu_leg(w, ends, queries, target_s=args.cpu_seconds, algo="fm")
-        scan = cpu_leg(w, ends, queries, target_s=min(4.0, args.cpu_seconds), algo="scan")
+        leg = cpu_leg(w, job.ends, queries, target_s=args.cpu_seconds, algo="fm")
+        scan = cpu_leg(w, job.ends, queries, target_s=min(4.0, args.cpu_seconds), algo="scan")
         cpu = {"value": leg["gcups"], "unit": "GCUPS", "cores": leg["threads"], "kind": "port", "algo": "fm-index",
                "sample": f"first {leg['reads']} of {n} sampled reads of both ends x all {q_start}+{q_end} query "
                          f"k-mers ({leg['columns']:.3g} columns, {leg['seconds']:.1f} s wall: index build "
@@ -563,43 +709,76 @@ def run_b200(args, w):
                              "sample": f"first {scan['reads']} reads of both ends, {scan['seconds']:.1f} s wall",
                              "note": CPU_NOTES["scan"]},
                "host_cpus": os.cpu_count(), "note": CPU_NOTES["fm"]}
-        # the CPU leg doubles as a spot check of the GPU counts on its sample
+        # the CPU leg doubles as a check of the GPU counts: a bounded sample of both ends against the oracle
         from oracle import orc
-        r = min(leg["reads"], 512)
-        chk = ApproxCounter(local_rank)
-        chk.upload_sample(np.ascontiguousarray(h_start[:r]))
-        got = chk.errorCount(queries[0], k)
-        codes, offs = orc.encode_matrix(h_start[:r])
-        want = orc.error_count(codes, offs, queries[0], k, fast=True)
-        chk.close()
-        if not np.array_equal(got, want):
-            raise SystemExit("bench.py: GPU counts differ from the oracle on the CPU-baseline sample")
+        r = min(n, 4096)
+        for e in (0, 1):
+            chk = ApproxCounter(local_rank)
+            chk.upload_sample(np.ascontiguousarray(job.ends[e][:r]))
+            got = chk.errorCount(queries[e], k)
+            chk.close()
+            codes, offs = orc.encode_matrix(job.ends[e][:r])
+            if not np.array_equal(got, orc.fm_index_error_count(codes, offs, queries[e], k)):
+                raise SystemExit("bench.py: PARITY FAILURE — GPU counts differ from the oracle on the check sample")
+        parity = f"ok: GPU counts == oracle (index-based CPU form) on the first {r} reads of both ends x all {q_start}+{q_end} k-mers"
+    if world == 1 and not args.no_extras:
+        # the floor: the same sample scanned for as many RANDOM k-mers with one k-mer per warp — no rows shared between
+        # k-mers, and unrelated k-mers leave little to skip
+        rng = np.random.default_rng(w["seed"])
+        rq = [np.unique(rng.integers(0, 1 << 62, 2 * len(q)).astype(np.uint64) & np.uint64((1 << (2 * k)) - 1 if k < 32 else (1 << 64) - 1))[: len(q)]
+              for q in queries]
+        job.set_queries(rq, options + [("shape_mask", 0)])
+        fr = timed_steps(torch, job, dist, flush, 3, 3)
+        floor = {"value": k * job.columns() * 3 / (fr["dev_ms"] / 1e3) / 1e9, "unit": "GCUPS", "ms_per_step": fr["dev_ms"] / 3,
+                 "executed_frac_of_lop3_peak": 32.0 * fr["stats"]["lop3_executed"] / (fr["kern_ms"] / 1e3) / lop3_peak,
+                 "what": "same sample, as many random k-mers, shape_mask=0 (one k-mer per warp): no row sharing"}
+        job.close()
+        # the same workload with the adapters at offsets uniform in 0..sl/2 instead of 0..7 (seed bit 40)
+        jw = Job(torch, dev, local_rank, stream, w, 0, n, seed=w["seed"] | (1 << 40))
+        jw.set_queries(jw.exact_queries(lim)[0], options)
+        wr = timed_steps(torch, jw, dist, flush, 5, 3)
+        wide = {"value": k * jw.columns() * 5 / (wr["dev_ms"] / 1e3) / 1e9, "unit": "GCUPS", "ms_per_step": wr["dev_ms"] / 5,
+                "executed_frac_of_lop3_peak": 32.0 * wr["stats"]["lop3_executed"] / (wr["kern_ms"] / 1e3) / lop3_peak,
+                "executed_over_planned": wr["stats"]["lop3_executed"] / max(wr["stats"]["lop3_planned"], 1.0),
+                "what": "same generator with the adapter offsets uniform in 0..sl/2 (default 0..7), own top-lim queries"}
+        jw.close()
+    else:
+        job.close()
 
     line = {
         "metric": "approx_count_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": w["text"] + ", both ends (start n x sl, end n x (sl+1))", "k": k,
-                   "reads_per_gpu": n, "reads_total": n_total, "sl": sl, "lim": lim, "queries": [q_start, q_end], "seed": w["seed"],
-                   "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset outside the event pairs)",
-                   "parallelism": f"reads sharded over {world} GPU(s), one all-reduce of Q u64 per end"},
+        "config": make_config(w, args.scaling, world),
+        "reads_per_gpu": n, "queries": [q_start, q_end],
+        "parallelism": f"reads sharded over {world} GPU(s); ONE ncclAllReduce of {q_start + q_end} u64 per step through the C ABI "
+                       "(apc_allreduce_counts)" if world > 1 else "1 GPU",
         "queries_per_s": (q_start + q_end) * args.steps / (dev_ms / 1e3),
         "columns_per_s": cols_job * args.steps / (dev_ms / 1e3),
-        "wall_s_timed_region": t_mark1 - t_mark0,
+        "wall_s_timed_region": res["t1"] - res["t0"],
         "exact_stage_ms": exact_ms,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                "path": "apc_upload_sample_async + apc_approx_count_async (C ABI, pinned host buffers, one stream per end), wall clock"},
-        "gpu_launches": n_launch,
+                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3, "frac_of_resident": e2e_value / value,
+                "path": "per step: apc_upload_sample_async + apc_set_queries + apc_scan per end (C ABI, pinned host buffers, one "
+                        "stream per end), apc_allreduce_counts, D2H of the counts; steps pipelined two deep; wall clock"},
+        "gpu_launches": res["launches"],
+        "parity_check": parity,
         "roofline": roofline,
+        # flat copies of the figures the review asked to see in the parsed line
+        "roofline_frac": roofline["frac"], "roofline_frac_planned": roofline["frac_planned"],
+        "roofline_frac_algorithmic": roofline["frac_algorithmic"],
+        "lop3_executed_per_step": 32.0 * st["lop3_executed"] / args.steps, "lop3_planned_per_step": 32.0 * st["lop3_planned"] / args.steps,
+        "lop3_one_kmer_per_warp_per_step": 32.0 * st["lop3_one_kmer_per_warp"] / args.steps,
+        "lop3_top_share_of_executed": st["lop3_top"] / max(st["lop3_executed"], 1.0),
+        "lop3_peak_measured_tops": lop3_peak / 1e12,
+        "floor_value": floor["value"] if floor else None, "floor": floor,
+        "wide_offset_value": wide["value"] if wide else None, "wide_offset": wide,
+        "c2_weak_value": c2["value"] if c2 else None, "c2_weak": c2,
         "cpu_baseline": cpu,
     }
     emit(line)
-    for c in ctxs:
-        c.close()
-    if world > 1:
-        dist.destroy_process_group()
+    dist.close()
     return 0
 
 
@@ -612,22 +791,24 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=25)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="C2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="C3")
     ap.add_argument("--scan-variant", type=int, default=0,
                     help="kernel A/B: 0 bit-sliced with k-mer pairing (default), 7 bit-sliced, 8 row-packed")
-    ap.add_argument("--reads", type=int, default=0, help="override the reads per GPU of the workload (C5 sweep)")
+    ap.add_argument("--reads", type=int, default=0, help="override the reads of the workload (C5 sweep)")
     ap.add_argument("--lim", type=int, default=0, help="override the number of query k-mers (C5 sweep)")
-    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
-                    help="weak: every rank holds its own n-read shard (default); strong: one n-read job split over the ranks")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="strong",
+                    help="strong (default): one n-read job split over the ranks; weak: every rank holds its own n-read shard")
     ap.add_argument("--plan-alive-pct", type=int, default=-1,
                     help="planner knob (apc_set_option plan_alive_pct): expected share of columns with live deep rows")
     ap.add_argument("--sg-per-job", type=int, default=0,
                     help="tuning knob (apc_set_option tiles_per_job): 1024-read super-groups per job, 0 = auto")
+    ap.add_argument("--no-graph", action="store_true", help="launch every scan directly (apc_set_option scan_graph 0)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size, seconds of CPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the floor / wide-offset / C2-weak side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = dict(WORKLOADS[args.workload])

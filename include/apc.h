@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define APC_VERSION 1
+#define APC_VERSION 2
 
 #define APC_OK 0
 #define APC_ERR_INVALID (-1)    /* bad argument (NULL, k outside [2,32], ...) */
@@ -37,6 +37,7 @@ extern "C" {
 #define APC_ERR_NO_QUERIES (-5) /* apc_scan before apc_set_queries */
 #define APC_ERR_NOMEM (-6)      /* host or device allocation failed */
 #define APC_ERR_CAPACITY (-7)   /* caller-provided output capacity too small */
+#define APC_ERR_COMM (-8)       /* NCCL unavailable or a collective failed; see apc_last_error */
 #define APC_MAXERR 2            /* compile-time edit bound, reference :25 */
 
 typedef struct apc_ctx apc_ctx;
@@ -141,7 +142,55 @@ int apc_get_counts(apc_ctx *ctx, uint64_t *counts_out);
 /* Device address of the context's own count buffer (n_kmers uint64). */
 uint64_t *apc_counts_device_ptr(apc_ctx *ctx);
 
+/* ---- multi-GPU: reads sharded, counts summed ------------------------------------
+ * Replaces the reference's only parallelism, the OpenMP team over k-mers that
+ * shares one index (:547-599) and its `omp critical` result merge (:595-596):
+ * the sampled reads are independent and a count is a sum over reads (:589-596),
+ * so every GPU scans one shard of the reads for ALL k-mers and the per-k-mer
+ * count vectors are summed with one small all-reduce over NVLink.  One context
+ * (= one GPU) is one rank; the ranks may live in one process (a host thread
+ * per GPU) or in one process per GPU.  libnccl.so.2 is loaded on first use.
+ *
+ *   rank 0:     apc_comm_unique_id(id)  -> hand `id` to every rank (any channel)
+ *   every rank: apc_comm_init_rank(ctx, n_ranks, rank, id)     (collective)
+ *   every rank: apc_scan_allreduce(ctx, NULL) [or apc_scan x2 ends, then one
+ *               apc_allreduce_counts over both vectors], apc_get_counts
+ */
+#define APC_COMM_ID_BYTES 128
+int apc_comm_unique_id(uint8_t id_out[APC_COMM_ID_BYTES]);
+int apc_comm_init_rank(apc_ctx *ctx, int n_ranks, int rank,
+                       const uint8_t id[APC_COMM_ID_BYTES]);
+int apc_comm_destroy(apc_ctx *ctx);
+/* rank / size of the context's communicator (0 / 1 without one) */
+int apc_comm_info(const apc_ctx *ctx, int *rank, int *n_ranks);
+/* In-place sum over the ranks of n uint64 at the DEVICE pointer d_counts (NULL:
+ * the context's own count buffer, n ignored), enqueued on the context's
+ * stream.  A context without a communicator returns APC_OK without doing
+ * anything, so single- and multi-GPU hosts share one code path. */
+int apc_allreduce_counts(apc_ctx *ctx, uint64_t *d_counts, uint64_t n);
+/* apc_scan followed by apc_allreduce_counts on the same stream: the whole
+ * errorCount of a sharded sample (:531-601), asynchronous. */
+int apc_scan_allreduce(apc_ctx *ctx, uint64_t *d_counts);
+
 int apc_last_timing(const apc_ctx *ctx, apc_timing *out);
+
+/* What the scans since the previous call cost on the integer ALU pipe, in LOP3
+ * warp instructions (x 32 = lane operations): the bit-sliced kernel spends 5
+ * per automaton row, text column and 1024 reads (minus 7 per unit and column
+ * for the constant cells of rows 0-1).  `executed` counts the rows the kernels
+ * really computed — the deep rows of a unit are skipped in the columns where
+ * nothing can reach them, which the kernels tally per job at run time —,
+ * `planned` every row of the scan plan in every column, `one_kmer_per_warp`
+ * the same without any row sharing between k-mers.  Synchronises the stream
+ * and resets the tally.  Zeros for the row-packed scan variants. */
+typedef struct apc_scan_stats {
+    uint64_t scans;
+    double lop3_executed;
+    double lop3_top;     /* part of `executed` spent in rows computed in every column */
+    double lop3_planned;
+    double lop3_one_kmer_per_warp;
+} apc_scan_stats;
+int apc_scan_stats_read(apc_ctx *ctx, apc_scan_stats *out);
 /* Kernels launched by the most recent apc_scan (no synchronisation). */
 uint64_t apc_last_scan_launches(const apc_ctx *ctx);
 
@@ -154,7 +203,10 @@ uint64_t apc_last_scan_launches(const apc_ctx *ctx);
  * unit shapes the default kernel may group k-mers into (bit s = shape s of
  * apc_plan_queries; default all, 0 = one k-mer per warp) and "plan_alive_pct":
  * the share of text columns (percent) in which the planner expects a unit's
- * deep rows to be computed; both applied at the next apc_set_queries. */
+ * deep rows to be computed; both applied at the next apc_set_queries.
+ * "scan_graph": 1 (default) = a scan that is issued again unchanged is captured
+ * in a CUDA graph and replayed from then on (one launch instead of up to 13 +
+ * fork/join events), 0 = always launch directly. */
 int apc_set_option(apc_ctx *ctx, const char *name, int64_t value);
 
 /* The scan plan apc_set_queries would build for these k-mers (needs no GPU):

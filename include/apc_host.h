@@ -62,7 +62,9 @@ int apch_sample(const apch_reads *r, uint64_t nb_sample, uint64_t cut, int bot,
 /* Synthetic ONT-like reads with planted adapters: read i of
  * stream `seed` is a pure function of (seed, i, sl).  apch_synth_ends writes
  * the sampled ends of reads [first, first+n) directly (n rows of sl, or sl+1
- * if bot); apch_synth_write writes the same reads as FASTA (or FASTQ). */
+ * if bot); apch_synth_write writes the same reads as FASTA (or FASTQ).  Bit 40
+ * of `seed` selects the wide variant of a stream: adapter offsets uniform in
+ * 0..sl/2 instead of 0..7. */
 int apch_synth_ends(uint64_t seed, uint64_t first, uint64_t n, uint32_t sl,
                     int bot, uint8_t *out);
 int apch_synth_write(const char *path, uint64_t seed, uint64_t n, uint32_t sl,

@@ -64,6 +64,12 @@ uint64_t orc_dimer_sum(uint64_t kmer, uint8_t k) {
     return sum;
 }
 
+/* the same over an array (test-side accelerator for top-N selection over 1e8 distinct k-mers) */
+void orc_dimer_sums(const uint64_t *kmers, uint64_t n, uint8_t k, uint32_t *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) out[i] = (uint32_t)orc_dimer_sum(kmers[i], k);
+}
+
 /* :214-234 */
 int orc_have_low_complexity(uint64_t kmer, uint8_t k, float threshold) {
     float s = (float)orc_dimer_sum(kmer, k) / (float)(2 * (k - 2));
@@ -167,6 +173,59 @@ uint64_t orc_count_kmers(const uint8_t *codes, const uint64_t *offs,
     for (uint64_t i = 0; i < count.cap; i++)
         if (count.used[i]) { (*keys)[j] = count.keys[i]; (*counts)[j] = count.vals[i]; j++; }
     orc_map_free(&count);
+    if (had_n_out) *had_n_out = had_n;
+    return n;
+}
+
+/* The same count with all host threads — set-up of bench.py's reference arm and of the full-size parity tests
+ * only (the reference's count_kmers is single-threaded, :487-519, and so is orc_count_kmers above; at C3/C4
+ * size that is minutes per end).  Every thread walks all reads with a rolling 2-bit window and keeps the
+ * k-mers of its own hash shard in its own map, so no two threads ever count the same k-mer; the shards are
+ * concatenated.  tests/test_oracle.py holds it equal to orc_count_kmers as a multiset. */
+uint64_t orc_count_kmers_mt(const uint8_t *codes, const uint64_t *offs, uint64_t n_reads, uint8_t k,
+                            float threshold, int nb_thread, uint64_t **keys, uint64_t **counts,
+                            uint64_t *had_n_out) {
+    int T = nb_thread > 0 ? nb_thread : omp_get_max_threads();
+    if (T < 1) T = 1;
+    orc_map *maps = (orc_map *)malloc((size_t)T * sizeof(orc_map));
+    uint64_t had_n = 0;
+    const uint64_t mask = k < 32 ? ((1ull << (2 * k)) - 1) : ~0ull;
+#pragma omp parallel num_threads(T) reduction(+ : had_n)
+    {
+        const int t = omp_get_thread_num();
+        const int nt = omp_get_num_threads();
+        if (t < T) {
+            orc_map_init(&maps[t], 1u << 16);
+            for (uint64_t r = 0; r < n_reads; r++) {
+                const uint8_t *seq = codes + offs[r];
+                const uint64_t len = offs[r + 1] - offs[r];
+                uint64_t w = 0, run = 0; /* run = letters since the last N */
+                for (uint64_t i = 0; i < len; i++) {
+                    if (seq[i] >= 4) { run = 0; w = 0; } else { w = ((w << 2) | seq[i]) & mask; run++; }
+                    if (i + 1 < k) continue;
+                    if (run < k) { if (t == 0) had_n++; continue; } /* window holds an N (:506) */
+                    uint64_t h = w * 0x9E3779B97F4A7C15ull;
+                    h ^= h >> 29;
+                    if ((int)(h % (uint64_t)nt) != t) continue;
+                    if (!orc_have_low_complexity(w, k, threshold)) orc_map_add(&maps[t], w, 1);
+                }
+            }
+        }
+        if (nt < T && t == 0) { /* fewer threads than asked for: the missing shards stay empty */
+            for (int m = nt; m < T; m++) orc_map_init(&maps[m], 16);
+        }
+    }
+    uint64_t n = 0;
+    for (int t = 0; t < T; t++) n += maps[t].n;
+    *keys = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
+    *counts = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
+    uint64_t j = 0;
+    for (int t = 0; t < T; t++) {
+        for (uint64_t i = 0; i < maps[t].cap; i++)
+            if (maps[t].used[i]) { (*keys)[j] = maps[t].keys[i]; (*counts)[j] = maps[t].vals[i]; j++; }
+        orc_map_free(&maps[t]);
+    }
+    free(maps);
     if (had_n_out) *had_n_out = had_n;
     return n;
 }

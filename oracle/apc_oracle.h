@@ -44,6 +44,7 @@ int orc_have_low_complexity(uint64_t kmer, uint8_t k, float threshold);
 float orc_get_complexity(uint64_t kmer, uint8_t k);
 /* integer numerator of the score: sum_v v*(v-1) over the 16 dimer bins. */
 uint64_t orc_dimer_sum(uint64_t kmer, uint8_t k);
+void orc_dimer_sums(const uint64_t *kmers, uint64_t n, uint8_t k, uint32_t *out);
 /* :283-302  returns 1 iff a sorts before b. */
 int orc_compare_count(uint64_t a_kmer, uint64_t a_count, uint64_t b_kmer,
                       uint64_t b_count, int k);
@@ -55,6 +56,10 @@ uint64_t orc_count_kmers(const uint8_t *codes, const uint64_t *offs,
                          uint64_t n_reads, uint8_t k, float threshold,
                          const uint64_t *forbidden, uint64_t n_forbidden,
                          uint64_t **keys, uint64_t **counts, uint64_t *had_n);
+/* same multiset with all host threads (set-up of the reference arm / full-size tests only) */
+uint64_t orc_count_kmers_mt(const uint8_t *codes, const uint64_t *offs, uint64_t n_reads, uint8_t k,
+                            float threshold, int nb_thread, uint64_t **keys, uint64_t **counts,
+                            uint64_t *had_n_out);
 
 /* :396-405  sort (kmer,count) pairs by CompareCount, keep first `limit`.
  * Sorts in place; returns the kept length. */

@@ -20,7 +20,7 @@ def build(force=False):
     need = force or not all(
         os.path.exists(os.path.join(_HERE, f)) for f in ("liborc.so", "libseqan_model.so", "libfm_index_model.so"))
     if not need:
-        for so, srcs in (("liborc.so", ("apc_oracle.c", "apc_oracle.h")),
+        for so, srcs in (("liborc.so", ("apc_oracle.c", "apc_oracle.h", "synth_reads.c")),
                          ("libseqan_model.so", ("seqan_model.cpp",)),
                          ("libfm_index_model.so", ("fm_index_model.cpp",))):
             t = os.path.getmtime(os.path.join(_HERE, so))
@@ -60,6 +60,10 @@ def lib():
                                       C.POINTER(C.POINTER(C.c_uint64)),
                                       C.POINTER(C.POINTER(C.c_uint64)),
                                       C.POINTER(C.c_uint64)]
+        L.orc_count_kmers_mt.restype = C.c_uint64
+        L.orc_count_kmers_mt.argtypes = [_u8p, _u64p, C.c_uint64, C.c_uint8, C.c_float, C.c_int,
+                                         C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.POINTER(C.c_uint64)),
+                                         C.POINTER(C.c_uint64)]
         L.orc_get_most_frequent.restype = C.c_uint64
         L.orc_get_most_frequent.argtypes = [_u64p, _u64p, C.c_uint64, C.c_uint64, C.c_int]
         L.orc_get_solid_kmers.restype = C.c_uint64
@@ -75,6 +79,9 @@ def lib():
         L.orc_export_counter.restype = C.c_int
         L.orc_export_counter.argtypes = [_u64p, _u64p, C.c_uint64, C.c_uint8, C.c_char_p]
         L.orc_num_threads.restype = C.c_int
+        L.orc_dimer_sums.argtypes = [_u64p, C.c_uint64, C.c_uint8, C.c_void_p]
+        L.orc_synth_ends.restype = C.c_int
+        L.orc_synth_ends.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -152,6 +159,14 @@ def dimer_sum(kmer, k):
     return int(lib().orc_dimer_sum(int(kmer), k))
 
 
+def dimer_sums(kmers, k):
+    """orc_dimer_sum (:216-231) over an array."""
+    kmers = np.ascontiguousarray(kmers, np.uint64)
+    out = np.zeros(len(kmers), np.uint32)
+    lib().orc_dimer_sums(kmers, len(kmers), k, out.ctypes.data)
+    return out
+
+
 def count_kmers(codes, offs, k, thr, forbidden=None):
     """-> (keys u64[D], counts u64[D], had_n) in unspecified order."""
     kp, cp = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)()
@@ -170,11 +185,49 @@ def count_kmers(codes, offs, k, thr, forbidden=None):
     return keys, cnts, int(had.value)
 
 
+def count_kmers_mt(codes, offs, k, thr, nb_thread=0):
+    """count_kmers with all host threads (same multiset; set-up of the reference arm and full-size tests)."""
+    if nb_thread <= 0:
+        nb_thread = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    kp, cp = C.POINTER(C.c_uint64)(), C.POINTER(C.c_uint64)()
+    had = C.c_uint64(0)
+    n = lib().orc_count_kmers_mt(codes, offs, len(offs) - 1, k, thr, int(nb_thread), C.byref(kp), C.byref(cp),
+                                 C.byref(had))
+    keys = np.ctypeslib.as_array(kp, shape=(max(n, 1),))[:n].copy()
+    cnts = np.ctypeslib.as_array(cp, shape=(max(n, 1),))[:n].copy()
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    libc.free(kp)
+    libc.free(cp)
+    return keys, cnts, int(had.value)
+
+
 def get_most_frequent(keys, counts, limit, k):
     keys = np.ascontiguousarray(keys, np.uint64).copy()
     counts = np.ascontiguousarray(counts, np.uint64).copy()
     n = lib().orc_get_most_frequent(keys, counts, len(keys), limit, k)
     return keys[:n], counts[:n]
+
+
+def get_most_frequent_fast(keys, counts, limit, k):
+    """get_most_frequent (:396-405) without sorting all D distinct k-mers (minutes at 1e8): a superset of the
+    first `limit` entries in CompareCount order (:275-305: count desc, complexity asc, k-mer desc) is cut out
+    with integer thresholds — the complexity score is the integer dimer sum over a constant (:227-233), so it
+    orders like the sum — and the comparator sort of get_most_frequent then runs on that superset only.
+    tests/test_oracle.py holds it equal to the full sort."""
+    keys = np.ascontiguousarray(keys, np.uint64)
+    counts = np.ascontiguousarray(counts, np.uint64)
+    if limit == 0 or len(keys) <= max(4 * limit, 1 << 16):
+        return get_most_frequent(keys, counts, limit, k)
+    cut = len(counts) - limit
+    c_star = np.partition(counts, cut)[cut]                 # limit-th largest count
+    above = counts > c_star
+    tie = np.flatnonzero(counts == c_star)
+    need = limit - int(above.sum())
+    sums = dimer_sums(keys[tie], k)
+    s_star = np.partition(sums, need - 1)[need - 1]
+    keep = np.concatenate([np.flatnonzero(above), tie[sums <= s_star]])
+    return get_most_frequent(keys[keep], counts[keep], limit, k)
 
 
 def get_solid_kmers(keys, counts, solid_km, k):
@@ -239,3 +292,13 @@ def export_counter(keys, counts, k, path):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def synth_ends(seed, first, n, sl, bot):
+    """Sampled ends of reads [first, first+n) of the synthetic stream `seed` (synth_reads.c):
+    uint8[n, sl] (start) or uint8[n, sl+1] (end) — the CPU side's own generator, byte-identical to the
+    product's apch_synth_ends (tests/test_host.py)."""
+    out = np.empty((int(n), int(sl) + (1 if bot else 0)), np.uint8)
+    if lib().orc_synth_ends(int(seed), int(first), int(n), int(sl), int(bool(bot)), out.ctypes.data) != 0:
+        raise MemoryError("orc_synth_ends")
+    return out

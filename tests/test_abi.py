@@ -37,7 +37,7 @@ def test_binding_tables_cover_the_headers(built):
 
 def test_headers_are_plain_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "apc.h"\n#include "apc_host.h"\nint main(void){return APC_VERSION==1?0:1;}\n')
+    src.write_text('#include "apc.h"\n#include "apc_host.h"\nint main(void){return APC_VERSION==2?0:1;}\n')
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
                     "-c", str(src), "-o", str(tmp_path / "t.o")], check=True)
 
@@ -49,7 +49,7 @@ def test_no_cpu_fallback(built):
         pytest.skip("a GPU is present")
     from approx_counter_b200 import ApcError, ApproxCounter, load
     lib = load()
-    assert lib.apc_version() == 1
+    assert lib.apc_version() == 2
     assert lib.apc_device_count() <= 0
     with pytest.raises(ApcError) as e:
         ApproxCounter(0)

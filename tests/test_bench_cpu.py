@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_reference_arm_prints_the_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C1",
                         "--reads", "2500", "--lim", "50", "--steps", "2", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+                       capture_output=True, text=True, timeout=300, cwd=ROOT,
+                       env=dict(os.environ, APC_LIB_PATH="/nonexistent/libapc.so"))  # loading the product would raise
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1                                    # exactly one JSON line on stdout
@@ -26,6 +27,13 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] == "port" and cb["algo"] == "fm-index" and cb["cores"] >= 1 and cb["value"] == d["value"]
     assert cb["index_build_s_per_step"] > 0 and cb["search_s_per_step"] > 0 and "sample" in cb
     assert d["config"]["k"] == 16 and "workload" in d["config"]
+    # both arms print the same `config` object (the driver compares them) ...
+    sys.path.insert(0, ROOT)
+    import bench
+    w = dict(bench.WORKLOADS["C1"], n=2500, lim=50)
+    w["text"] = f"C5 sweep point on C1: -sn {w['n']} -sl {w['sl']} -lim {w['lim']}, k={w['k']}"
+    assert d["config"] == bench.make_config(w, "strong", 1)
+    # ... and the reference arm never loads the product library (APC_LIB_PATH above points nowhere)
 
 
 def test_other_ranks_of_the_reference_arm_do_nothing():
@@ -40,7 +48,7 @@ def test_cpu_legs_agree(built):
     import bench
     from oracle import orc
     w = dict(bench.WORKLOADS["C1"], n=1500, lim=40)
-    ends, _ = bench.make_ends(w, 0)
+    ends = (orc.synth_ends(w["seed"], 0, w["n"], w["sl"], False), orc.synth_ends(w["seed"], 0, w["n"], w["sl"], True))
     queries = bench.reference_queries(w, ends)
     assert all(len(q) == 40 for q in queries)
     for sample, km in zip(ends, queries):

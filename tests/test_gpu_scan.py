@@ -347,3 +347,67 @@ def test_deep_rows_wake_and_drain(counter, k):
             assert np.array_equal(counter.errorCount(kmers, k), want), name
         finally:
             counter.set_option("shape_mask", 0xFFFFFFFF)
+
+
+def test_nccl_communicator_through_the_abi_single_rank(built):
+    """apc_comm_unique_id / apc_comm_init_rank / apc_scan_allreduce with a communicator of ONE rank: libnccl is
+    loaded by libapc itself and the all-reduce really runs on the context's stream — the driver's single-GPU
+    box cannot run the multi-rank tests (tests/test_gpu_multi.py), this keeps the ABI path under its eyes."""
+    from approx_counter_b200 import ApproxCounter
+    rng = np.random.default_rng(12)
+    sample = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=(3000, 100))
+    sample[::3, 7:23] = np.frombuffer(b"AATGTACTTCGTTCAG", np.uint8)
+    kmers = np.array([orc.dna2int("AATGTACTTCGTTCAG"), orc.dna2int("AATGTACTTCGTTCAT"), 99, 12345], np.uint64)
+    codes, offs = orc.encode_matrix(sample)
+    want = orc.error_count(codes, offs, kmers, 16, fast=True)
+    with ApproxCounter(0) as c:
+        assert c.comm_info() == (0, 1)
+        c.allreduce_counts()                         # no communicator: a no-op, not an error
+        c.comm_init_rank(1, 0, ApproxCounter.comm_unique_id())
+        assert c.comm_info() == (0, 1)
+        c.upload_sample(sample)
+        c.set_queries(kmers, 16)
+        for _ in range(3):                           # direct launches, graph capture, graph replay
+            c.scan_allreduce()
+            assert np.array_equal(c.get_counts(), want)
+        c.comm_destroy()
+        c.scan_allreduce()
+        assert np.array_equal(c.get_counts(), want)
+
+
+def test_scan_graph_replay_and_statistics(built):
+    """A scan issued again unchanged is captured in a CUDA graph and replayed; any change (queries, sample,
+    options, destination) falls back to direct launches.  The executed-row tally of the kernels is the same
+    whichever way the scan was launched and lies between the top rows and the whole plan."""
+    from approx_counter_b200 import ApproxCounter
+    sample = np.ascontiguousarray(orc.synth_ends(4321, 0, 5000, 100, False))
+    codes, offs = orc.encode_matrix(sample)
+    adapter = "AATGTACTTCGTTCAGTTACGTATTGCT"
+    kmers = sorted({orc.dna2int(adapter[i:i + 16][:p] + c + adapter[i:i + 16][p + 1:])
+                    for i in range(8) for p in range(16) for c in "ACGT"})
+    kmers = np.array(kmers, np.uint64)
+    want = orc.error_count(codes, offs, kmers, 16, fast=True)
+    per_scan = []
+    for graph in (1, 0):
+        with ApproxCounter(0) as c:
+            c.set_option("scan_graph", graph)
+            c.upload_sample(sample)
+            c.set_queries(kmers, 16)
+            c.scan_stats()
+            for i in range(4):
+                c.scan()
+                assert np.array_equal(c.get_counts(), want), (graph, i)
+            st = c.scan_stats()
+            assert st["scans"] == 4
+            assert st["lop3_top"] < st["lop3_executed"] < st["lop3_planned"] < st["lop3_one_kmer_per_warp"]
+            per_scan.append(st["lop3_executed"] / 4)
+            # a change between scans: other queries, then the first set again
+            c.set_queries(kmers[::-1].copy(), 16)
+            c.scan()
+            assert np.array_equal(c.get_counts(), want[::-1])
+            c.set_option("scan_n_reads", 2048)
+            c.scan()
+            c.scan()
+            part = orc.error_count(codes[: 2048 * 100], offs[:2049], kmers[::-1].copy(), 16, fast=True)
+            assert np.array_equal(c.get_counts(), part)
+    assert per_scan[0] == per_scan[1]

@@ -262,3 +262,12 @@ def test_parallel_parser_multiline_fastq(host, tmp_path, monkeypatch, mmap_bytes
                 got = None
             bad += got != want
     assert bad == 0
+
+
+def test_oracle_synth_equals_host_synth(host):
+    """The CPU side generates its workloads with oracle/synth_reads.c (so that the reference arm never loads
+    the product library); the two generators must agree byte for byte."""
+    for seed, first, n, sl in ((1001, 0, 300, 100), (1003, 12345, 200, 150), (1004, 999_000, 100, 200), (7, 5, 50, 16),
+                               (1002 | 1 << 40, 0, 300, 100)):   # bit 40: adapter offsets uniform in 0..sl/2
+        for bot in (False, True):
+            assert np.array_equal(orc.synth_ends(seed, first, n, sl, bot), host.synth_ends(seed, first, n, sl, bot))

@@ -303,3 +303,34 @@ def test_split_identity():
             codes, _ = orc.encode([text])
             want = orc.min_infix_distance(codes, orc.dna2int(kmer), k)  # clamped at 3
             assert min(split, 3) == want, (kmer, text, cut, split, want)
+
+
+def test_get_most_frequent_fast_equals_full_sort():
+    """The threshold-cut form used at full size (tests/test_gpu_fullsize.py, bench.py's reference arm) returns
+    exactly what the comparator sort of all distinct k-mers returns, ties and all."""
+    rng = np.random.default_rng(31)
+    for k, n in ((16, 300_000), (20, 200_000), (5, 1024)):
+        mask = np.uint64((1 << (2 * k)) - 1)
+        keys = np.unique(rng.integers(0, 1 << 62, n).astype(np.uint64) & mask)
+        cnts = np.ones(len(keys), np.uint64)
+        hot = rng.choice(len(keys), min(500, len(keys) // 2), replace=False)
+        cnts[hot] = rng.integers(1, 6, len(hot)).astype(np.uint64)
+        for lim in (1, 50, 400, 2000):
+            a = orc.get_most_frequent_fast(keys, cnts, lim, k)
+            b = orc.get_most_frequent(keys, cnts, lim, k)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_count_kmers_mt_equals_count_kmers():
+    rng = np.random.default_rng(5)
+    for k, n, L in ((16, 3000, 100), (20, 500, 151), (32, 300, 201), (4, 200, 30)):
+        sample = orc.synth_ends(77 + k, 0, n, L, False)
+        sample[rng.integers(0, n, 40), rng.integers(0, L, 40)] = ord("N")
+        codes, offs = orc.encode_matrix(sample)
+        thr = orc.adjust_threshold(1.0, 16, k)
+        a = orc.count_kmers(codes, offs, k, thr)
+        for threads in (1, 3, 8):
+            b = orc.count_kmers_mt(codes, offs, k, thr, threads)
+            assert a[2] == b[2]
+            oa, ob = np.argsort(a[0]), np.argsort(b[0])
+            assert np.array_equal(a[0][oa], b[0][ob]) and np.array_equal(a[1][oa], b[1][ob])
