@@ -135,15 +135,18 @@ class ApproxCounter:
         """counts[i] = sum_e |reads flagged at error level e| for kmers[i] (host in/out)."""
         km = _as_kmers(kmers)
         out = np.zeros(len(km), np.uint64)
+        self._n_kmers = len(km)
         self._check(self._lib.apc_approx_count(self._h, int(k), km.ctypes.data, len(km), out.ctypes.data))
         return out
 
     def errorCount_ptr(self, kmers_ptr, n_kmers, k, counts_ptr):
+        self._n_kmers = int(n_kmers)
         self._check(self._lib.apc_approx_count(self._h, int(k), C.c_void_p(int(kmers_ptr)), int(n_kmers),
                                                C.c_void_p(int(counts_ptr))))
 
     def errorCount_ptr_async(self, kmers_ptr, n_kmers, k, counts_ptr):
         """Enqueue only; counts are valid after sync()."""
+        self._n_kmers = int(n_kmers)
         self._check(self._lib.apc_approx_count_async(self._h, int(k), C.c_void_p(int(kmers_ptr)), int(n_kmers),
                                                      C.c_void_p(int(counts_ptr))))
 
@@ -252,3 +255,14 @@ def plan_queries(kmers, k):
     if rc != 0:
         raise ApcError(rc, "apc_plan_queries")
     return {"order": order, "reversed": rev, "units": units, "shape_t": st, "shape_g": sg}
+
+
+def plan_summary(kmers, k):
+    """How the default kernel splits these k-mers between families and one-warp units (apc_plan_summary)."""
+    lib = _lib.load()
+    km = _as_kmers(kmers)
+    out = [C.c_uint32() for _ in range(4)]
+    rc = lib.apc_plan_summary(int(k), km.ctypes.data, len(km), *[C.byref(o) for o in out])
+    if rc != 0:
+        raise ApcError(rc, "apc_plan_summary")
+    return dict(zip(("family_passes", "family_units", "family_kmers", "unit_kmers"), (o.value for o in out)))

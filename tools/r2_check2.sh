@@ -1,0 +1,12 @@
+#!/bin/bash
+# GPU call: parity of the family kernel (scan + fuzz + properties tests), then A/B family on/off on C2 and C3
+set -u
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_scan.py tests/test_gpu_fuzz.py tests/test_gpu_properties.py tests/test_gpu_fullsize.py -m gpu -x -q 2>&1 | tail -8
+for w in C2 C3; do
+  for fam in "" "--no-family"; do
+    python bench.py --workload $w --steps 10 --no-cpu-baseline --no-extras $fam > gpurun_out/r02b_${w}${fam}.json 2> gpurun_out/r02b_${w}${fam}.err
+    echo "bench $w $fam rc=$? $(python -c "import json,sys; d=json.load(open('gpurun_out/r02b_${w}${fam}.json')); print(round(d['value']), round(d['ms_per_step'],3), 'frac', round(d['roofline_frac'],3), 'exec/step', d['lop3_executed_per_step'], 'top', round(d['lop3_top_share_of_executed'],3))" 2>&1 | tail -1)"
+    tail -2 gpurun_out/r02b_${w}${fam}.err
+  done
+done
