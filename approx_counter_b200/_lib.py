@@ -54,7 +54,6 @@ SYMBOLS = {
     "apc_approx_count_async": (C.c_int, [_vp, C.c_uint8, _vp, C.c_uint32, _vp]),
     "apc_set_queries": (C.c_int, [_vp, C.c_uint8, _vp, C.c_uint32]),
     "apc_plan_queries": (C.c_int, [C.c_uint8, _vp, C.c_uint32, _vp, _vp, _vp, _vp, _vp]),
-    "apc_plan_summary": (C.c_int, [C.c_uint8, _vp, C.c_uint32, _vp, _vp, _vp, _vp]),
     "apc_scan": (C.c_int, [_vp, _vp]),
     "apc_get_counts": (C.c_int, [_vp, _vp]),
     "apc_counts_device_ptr": (_vp, [_vp]),

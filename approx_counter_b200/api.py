@@ -255,14 +255,3 @@ def plan_queries(kmers, k):
     if rc != 0:
         raise ApcError(rc, "apc_plan_queries")
     return {"order": order, "reversed": rev, "units": units, "shape_t": st, "shape_g": sg}
-
-
-def plan_summary(kmers, k):
-    """How the default kernel splits these k-mers between families and one-warp units (apc_plan_summary)."""
-    lib = _lib.load()
-    km = _as_kmers(kmers)
-    out = [C.c_uint32() for _ in range(4)]
-    rc = lib.apc_plan_summary(int(k), km.ctypes.data, len(km), *[C.byref(o) for o in out])
-    if rc != 0:
-        raise ApcError(rc, "apc_plan_summary")
-    return dict(zip(("family_passes", "family_units", "family_kmers", "unit_kmers"), (o.value for o in out)))

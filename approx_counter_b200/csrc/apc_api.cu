@@ -131,12 +131,12 @@ int apc_create(int device, apc_ctx **out) {
     for (int i = 0; i < 8 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_table, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_job_counter, apc::kBsSlots * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMemset(c->d_job_counter, 0, apc::kBsSlots * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_job_counter, (apc::kBsShapes + 1) * sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMemset(c->d_job_counter, 0, (apc::kBsShapes + 1) * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_deep_lop3, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(c->d_deep_lop3, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->bs_fork, cudaEventDisableTiming);
-    for (int i = 0; i < apc::kBsSlots - 1 && e == cudaSuccess; i++) {
+    for (int i = 0; i < apc::kBsShapes && e == cudaSuccess; i++) {
         e = cudaStreamCreateWithFlags(&c->bs_streams[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->bs_join[i], cudaEventDisableTiming);
     }
@@ -163,7 +163,6 @@ void apc_destroy(apc_ctx *c) {
     cudaFree(c->d_counts);
     cudaFree(c->d_job_counter);
     cudaFree(c->d_deep_lop3);
-    cudaFree(c->d_fam);
     if (c->scan_graph) cudaGraphExecDestroy(c->scan_graph);
     apc_comm_destroy(c);
     cudaFree(c->d_stage);
@@ -174,7 +173,7 @@ void apc_destroy(apc_ctx *c) {
         if (e) cudaEventDestroy(e);
     if (c->ev_table) cudaEventDestroy(c->ev_table);
     if (c->bs_fork) cudaEventDestroy(c->bs_fork);
-    for (int i = 0; i < apc::kBsSlots - 1; i++) {
+    for (int i = 0; i < apc::kBsShapes; i++) {
         if (c->bs_join[i]) cudaEventDestroy(c->bs_join[i]);
         if (c->bs_streams[i]) cudaStreamDestroy(c->bs_streams[i]);
     }
@@ -347,54 +346,30 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
         APC_CUDA(c, cudaEventSynchronize(c->ev_table));
         c->table_copy_pending = false;
     }
-    // + room for the family tables: at most 16 padded tail slots of 12 bytes per k-mer, a unit and a pass per k-mer
-    const size_t pinned_need = table_words * sizeof(uint32_t) + (bs ? (size_t)n_kmers * (16 * 12 + sizeof(apc::FamUnit) + sizeof(apc::FamPass)) + 64 : 0);
-    if (pinned_need > c->pinned_cap) {
+    if (table_words * sizeof(uint32_t) > c->pinned_cap) {
         if (c->h_pinned) APC_CUDA(c, cudaFreeHost(c->h_pinned));
         c->h_pinned = nullptr;
         c->pinned_cap = 0;
-        const size_t cap = std::max<size_t>(pinned_need * 2, 1 << 16);
+        const size_t cap = std::max<size_t>(table_words * sizeof(uint32_t) * 2, 1 << 16);
         cudaError_t e = cudaMallocHost(&c->h_pinned, cap);
         if (e != cudaSuccess) return apc::fail(c, APC_ERR_NOMEM, "cudaMallocHost", e);
         c->pinned_cap = cap;
     }
     void *d_dst = nullptr;
-    uint32_t n_groups = 0, n_generic = n_kmers;
+    uint32_t n_groups = 0;
     uint32_t units[apc::kBsShapes] = {};
-    apc::FamPlan fam;
-    size_t fam_bytes[4] = {0, 0, 0, 0}, fam_total = 0;
-    char *fam_host = nullptr;
     if (bs) {
         // k-mers in scan order (units of prefix- or suffix-sharing k-mers first, shape by shape), then the
         // index of each in the caller's order; bit 31 marks the members of a unit that is scanned backwards
         std::vector<uint32_t> order;
         std::vector<uint8_t> reversed;
-        const bool want_families = variant.pairing() && c->opt_family && c->opt_shape_mask == 0xFFFFFFFFu;
         apc::bs_group_queries(kmers, n_kmers, k, variant.pairing() ? c->opt_shape_mask : 0u, (float)c->opt_alive_pct / 100.f,
-                              order, reversed, units, want_families ? &fam : nullptr);
-        n_generic = (uint32_t)order.size();
+                              order, reversed, units);
         uint64_t *hk = (uint64_t *)c->h_pinned;
-        uint32_t *hp = (uint32_t *)(hk + n_generic);
-        for (uint32_t i = 0; i < n_generic; i++) {
+        uint32_t *hp = (uint32_t *)(hk + n_kmers);
+        for (uint32_t i = 0; i < n_kmers; i++) {
             hk[i] = reversed[i] ? apc::bs_reverse_kmer(kmers[order[i]], k) : kmers[order[i]];
             hp[i] = order[i] | (reversed[i] ? 0x80000000u : 0u);
-        }
-        // the families' tables follow in the same pinned buffer: k-mers, passes, units, perm (8-byte items first)
-        fam_bytes[0] = fam.kmers.size() * sizeof(uint64_t);
-        fam_bytes[1] = fam.passes.size() * sizeof(apc::FamPass);
-        fam_bytes[2] = fam.units.size() * sizeof(apc::FamUnit);
-        fam_bytes[3] = fam.perm.size() * sizeof(uint32_t);
-        fam_total = fam_bytes[0] + fam_bytes[1] + fam_bytes[2] + fam_bytes[3];
-        if (fam_total) {
-            if (table_words * sizeof(uint32_t) + fam_total + 16 > c->pinned_cap)
-                return apc::fail(c, APC_ERR_NOMEM, "family tables exceed the staging buffer (internal)");
-            fam_host = (char *)c->h_pinned + ((table_words * sizeof(uint32_t) + 15) & ~(size_t)15);
-            char *w = fam_host;
-            std::memcpy(w, fam.kmers.data(), fam_bytes[0]); w += fam_bytes[0];
-            std::memcpy(w, fam.passes.data(), fam_bytes[1]); w += fam_bytes[1];
-            std::memcpy(w, fam.units.data(), fam_bytes[2]); w += fam_bytes[2];
-            std::memcpy(w, fam.perm.data(), fam_bytes[3]);
-            if ((st = apc::grow(c, c->d_fam, c->fam_cap, fam_total))) return st;
         }
         n_groups = n_kmers;
         if ((st = apc::grow(c, c->d_kmers, c->kmers_cap, table_words * sizeof(uint32_t)))) return st;
@@ -409,20 +384,8 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
     if (table_words) {
         APC_CUDA(c, cudaMemcpyAsync(d_dst, c->h_pinned, table_words * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                     c->stream));
-        if (fam_total) APC_CUDA(c, cudaMemcpyAsync(c->d_fam, fam_host, fam_total, cudaMemcpyHostToDevice, c->stream));
         APC_CUDA(c, cudaEventRecord(c->ev_table, c->stream));
         c->table_copy_pending = true;
-    }
-    {
-        const char *d = (const char *)c->d_fam;
-        c->d_fam_kmers = (const uint64_t *)d;
-        c->d_fam_passes = (const apc::FamPass *)(d + fam_bytes[0]);
-        c->d_fam_units = (const apc::FamUnit *)(d + fam_bytes[0] + fam_bytes[1]);
-        c->d_fam_perm = (const uint32_t *)(d + fam_bytes[0] + fam_bytes[1] + fam_bytes[2]);
-        c->fam_passes = fam_total ? (uint32_t)fam.passes.size() : 0;
-        c->fam_lop3_top_per_col = fam.lop3_top_per_col;
-        c->fam_lop3_all_per_col = fam.lop3_all_per_col;
-        c->n_generic = n_generic;
     }
     c->n_kmers = n_kmers;
     c->variant = variant;
@@ -544,25 +507,6 @@ int apc_scan(apc_ctx *c, uint64_t *d_counts) {
     return APC_OK;
 }
 
-int apc_plan_summary(uint8_t k, const uint64_t *kmers, uint32_t n_kmers, uint32_t *n_family_passes, uint32_t *n_family_units,
-                     uint32_t *n_family_kmers, uint32_t *n_unit_kmers) {
-    if (k < 2 || k > 32 || (!kmers && n_kmers) || n_kmers > 0x7FFFFFFFu) return APC_ERR_INVALID;
-    try {
-        std::vector<uint32_t> order;
-        std::vector<uint8_t> reversed;
-        uint32_t units[apc::kBsShapes];
-        apc::FamPlan fam;
-        apc::bs_group_queries(kmers, n_kmers, k, 0xFFFFFFFFu, (float)apc::kBsAlivePct / 100.f, order, reversed, units, &fam);
-        if (n_family_passes) *n_family_passes = (uint32_t)fam.passes.size();
-        if (n_family_units) *n_family_units = (uint32_t)fam.units.size();
-        if (n_family_kmers) *n_family_kmers = fam.n_members;
-        if (n_unit_kmers) *n_unit_kmers = (uint32_t)order.size();
-    } catch (...) {
-        return APC_ERR_NOMEM;
-    }
-    return APC_OK;
-}
-
 int apc_scan_allreduce(apc_ctx *c, uint64_t *d_counts) {
     int st = apc_scan(c, d_counts);
     if (st) return st;
@@ -640,10 +584,6 @@ int apc_last_timing(const apc_ctx *cc, apc_timing *out) {
 int apc_set_option(apc_ctx *c, const char *name, int64_t value) {
     if (!c || !name) return APC_ERR_INVALID;
     c->plan_gen++; // any option may change what a scan launches
-    if (!std::strcmp(name, "family")) { // takes effect at the next apc_set_queries
-        c->opt_family = value != 0;
-        return APC_OK;
-    }
     if (!std::strcmp(name, "scan_graph")) {
         c->opt_graph = value != 0;
         return APC_OK;

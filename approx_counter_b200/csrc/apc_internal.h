@@ -37,7 +37,6 @@ struct BsShape {
     int t, g;
 };
 constexpr int kBsShapes = 12;
-constexpr int kBsSlots = kBsShapes + 2; // concurrent launches of one scan: the families, one per shape, the single k-mers
 constexpr int kBsMaxRows = 48;
 constexpr int kBsAlivePct = 30;
 constexpr BsShape bs_shape(int k, int s) {
@@ -66,54 +65,6 @@ constexpr int bs_check_row_host(int k) {
 #define APC_BS_PREFETCH_PAIRS 1
 #endif
 constexpr int kBsPadCols = 2 * APC_BS_PREFETCH_PAIRS;
-// ---- family form of the bit-sliced scan (family_core.cuh) ----------------------------------------------------
-// A family = query k-mers (in one direction) that share their first bases; its trunk (the member on the heavy path
-// of the family's prefix tree) is scanned once per 1024 reads by the producer warp of a CTA, the other members form
-// units — a stretch of ST rows shared inside the unit, then G private tails of T rows — that attach to trunk row
-// a - 1, a = K - T - ST, and are scanned by the CTA's consumer warps.
-struct FamShape {
-    int st, t, g;
-};
-constexpr int kFamShapes = 22;
-constexpr FamShape fam_shape(int s) {
-    const FamShape table[kFamShapes] = {{0, 8, 4},  {1, 8, 4},  {0, 6, 6},  {0, 6, 3},  {2, 6, 3}, {0, 5, 6}, {3, 5, 6}, {0, 3, 8},
-                                        {0, 3, 4},  {2, 3, 4},  {3, 3, 8},  {0, 2, 16}, {3, 2, 16}, {6, 2, 16}, {0, 2, 8}, {4, 2, 8},
-                                        {2, 1, 4},  {6, 1, 4},  {9, 1, 4},  {0, 1, 4},  {0, 12, 4}, {0, 16, 2}};
-    return table[s];
-}
-__host__ __device__ inline int fam_shape_g(int s) { return s >= 0 && s < kFamShapes ? fam_shape(s).g : 0; }
-// trunk rows K-1-fam_pub(K) .. K-2 are published (a unit attaches to one of them): half the k-mer, what the shared
-// memory of an SM holds next to the parked unit states
-constexpr int fam_pub(int k) { return k >= 28 ? 16 : k >= 18 ? 10 : 8; }
-constexpr int fam_state_rows(int k) { return k >= 28 ? 232 : 288; } // unit rows parked in shared memory per pass
-constexpr int kFamMinK = 16;                                         // families are planned for k >= 16
-constexpr bool fam_shape_valid(int k, int s) {
-#ifdef APC_FAM_ONLY_SHAPE
-    if (s != APC_FAM_ONLY_SHAPE && s != APC_FAM_ONLY_SHAPE + 1) return false; // experiment: instruction footprint
-#endif
-    return k >= kFamMinK && fam_shape(s).st + fam_shape(s).t <= fam_pub(k) && k - fam_shape(s).st - fam_shape(s).t >= 3;
-}
-struct FamUnit {
-    uint32_t first_kmer; // index of the unit's first k-mer in the family k-mer / perm arrays (G entries, padded)
-    uint16_t shape;
-    uint16_t state_row;  // first row of the unit's parking area in shared memory
-};
-struct FamPass { // one CTA job per (pass, 1024 reads)
-    uint64_t trunk;      // the trunk k-mer, reversed if the family walks the text backwards
-    uint32_t trunk_perm; // its index in the caller's order, bit 31 = backwards
-    uint32_t unit_first; // first unit of the pass in the unit array
-    uint32_t warp_end[7]; // consumer w scans units [warp_end[w-1], warp_end[w]) of the pass (relative to unit_first)
-    uint32_t pad_;
-};
-struct FamPlan {
-    std::vector<FamPass> passes;
-    std::vector<FamUnit> units;
-    std::vector<uint64_t> kmers; // oriented
-    std::vector<uint32_t> perm;  // caller's index, 0xFFFFFFFF = padding
-    double lop3_top_per_col = 0., lop3_all_per_col = 0.; // per text column and 1024 reads, all passes
-    uint32_t n_members = 0;                                // query k-mers the families hold (trunks included)
-};
-
 struct BsRange { // super-groups (1024 reads) and reads [lo, hi) of one scan
     uint32_t sg_first, n_sg;
     uint64_t lo, hi;
@@ -187,25 +138,14 @@ struct Ctx {
     unsigned long long *d_counts = nullptr; // [n_groups * queries_per_group]
     size_t counts_cap = 0;
     unsigned int *d_job_counter = nullptr;  // job queue heads of the persistent scan kernels (self re-arming), one per
-                                            // concurrent launch: [kBsSlots]
-    // family form (family_core.cuh): passes, units, k-mers and perm of the families in one device buffer
-    void *d_fam = nullptr;
-    size_t fam_cap = 0;
-    const FamPass *d_fam_passes = nullptr;
-    const FamUnit *d_fam_units = nullptr;
-    const uint64_t *d_fam_kmers = nullptr;
-    const uint32_t *d_fam_perm = nullptr;
-    uint32_t fam_passes = 0;
-    uint32_t n_generic = 0; // k-mers in d_kmers (the rest of the n_kmers queries are scanned as families)
-    double fam_lop3_top_per_col = 0., fam_lop3_all_per_col = 0.;
-    int opt_family = 1;     // 0 = never plan families
+                                            // concurrent launch: [kBsShapes + 1]
     unsigned long long *d_deep_lop3 = nullptr; // LOP3 warp instructions the scan kernels spent on deep rows (dead-row
                                                // skipping makes that data dependent) since the last apc_scan_stats_read
     // host side of the same statistics, accumulated per scan from the plan
     mutable double stat_lop3_top = 0., stat_lop3_all = 0., stat_lop3_single = 0.;
     mutable uint64_t stat_scans = 0;
-    cudaStream_t bs_streams[kBsSlots - 1] = {}; // side streams of the bit-sliced scan (one launch per shape, concurrent)
-    cudaEvent_t bs_join[kBsSlots - 1] = {};
+    cudaStream_t bs_streams[kBsShapes] = {}; // side streams of the bit-sliced scan (one launch per shape, concurrent)
+    cudaEvent_t bs_join[kBsShapes] = {};
     cudaEvent_t bs_fork = nullptr;
 
     // CUDA graph of the launches of one scan (fork, one kernel per shape in use, join): captured when the same
@@ -277,8 +217,7 @@ cudaError_t launch_build_planes(const Ctx &c);
 cudaError_t launch_bs_scan(const Ctx &c, uint64_t read_lo, uint64_t read_hi, unsigned long long *d_counts,
                            uint32_t sg_per_job, uint64_t *launches);
 void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_mask, float alive,
-                      std::vector<uint32_t> &order, std::vector<uint8_t> &reversed, uint32_t (&units)[kBsShapes],
-                      FamPlan *families = nullptr);
+                      std::vector<uint32_t> &order, std::vector<uint8_t> &reversed, uint32_t (&units)[kBsShapes]);
 uint64_t bs_reverse_kmer(uint64_t kmer, int k);
 
 // exact_kernels.cu

@@ -445,7 +445,7 @@ static cudaError_t bs_launch_one(BsLaunchCtx &l, Kernel kernel, int mb, uint32_t
     const uint32_t spj = bs_sg_per_job(l, n_units, mb);
     const uint64_t jobs = (uint64_t)((l.r.n_sg + spj - 1) / spj) * n_units;
     if (jobs > 0x7FFFFFFFull) return cudaErrorInvalidConfiguration;
-    const uint32_t *perm = reinterpret_cast<const uint32_t *>(c.d_kmers + c.n_generic);
+    const uint32_t *perm = reinterpret_cast<const uint32_t *>(c.d_kmers + c.n_kmers);
     const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)c.sm_count * mb, jobs);
     const int slot = l.slot++;
     cudaStream_t s = c.stream;
@@ -487,23 +487,17 @@ static cudaError_t bs_launch_shapes(BsLaunchCtx &l, uint32_t &first_kmer) {
 }
 
 template <int K>
-static cudaError_t launch_family_k(BsLaunchCtx &l); // family_core.cuh
-
-template <int K>
 static cudaError_t launch_bs_k(BsLaunchCtx &l) {
     const Ctx &c = *l.c;
     uint32_t first = 0;
-    // the families first (one CTA per SM), then the unit shapes in table order (the heaviest units first), then
-    // the k-mers that found no partner
-    cudaError_t e = launch_family_k<K>(l);
+    // shapes in table order (the heaviest units first), then the k-mers that found no partner
+    cudaError_t e = bs_launch_shapes<K, 0>(l, first);
     if (e != cudaSuccess) return e;
-    e = bs_launch_shapes<K, 0>(l, first);
-    if (e != cudaSuccess) return e;
-    if (first < c.n_generic) {
+    if (first < c.n_kmers) {
         // registers: 3K of state + the row masks of two columns in flight (ptxas wants about 6K + 26);
         // CTAs (= warps) per SM chosen so that nothing spills
         constexpr int MB = bs_warps_per_sm_c(K);
-        e = bs_launch_one(l, bs_scan_kernel<K, MB>, MB, first, c.n_generic - first, bs_rows_split(K, K, 1, bs_check_row(K)));
+        e = bs_launch_one(l, bs_scan_kernel<K, MB>, MB, first, c.n_kmers - first, bs_rows_split(K, K, 1, bs_check_row(K)));
     }
     return e;
 }

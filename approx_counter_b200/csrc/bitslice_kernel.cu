@@ -188,182 +188,6 @@ void bs_sort_keys(std::vector<BsKey> &a, std::vector<BsKey> &tmp, int k) {
 
 } // namespace
 
-// ---- families (family_core.cuh) ---------------------------------------------------------------------------
-namespace {
-
-inline int bs_lcp(uint64_t a, uint64_t b, int k) { // common prefix of two k-mers, in bases
-    const uint64_t x = a ^ b;
-    if (!x) return k;
-    return k - (64 - __builtin_clzll(x) + 1) / 2;
-}
-
-struct FamUnitPlan {
-    uint32_t first, count; // members [first, first + count) of the family's sorted member list
-    int shape;
-    float cost;            // row-equivalents per column
-};
-
-// rows of a family unit of shape s that are computed in every column / only while alive
-inline void fam_unit_rows(int k, int s, int &top, int &deep) {
-    const FamShape sh = fam_shape(s);
-    const int a = k - sh.t - sh.st, m = bs_check_row_host(k);
-    const int tops = std::max(0, std::min(sh.st, m - a)), topt = std::max(0, std::min(sh.t, m - a - sh.st));
-    top = tops + sh.g * topt;
-    deep = sh.st + sh.g * sh.t - top;
-}
-
-// Plans the families of one direction.  v[0..n) are the (oriented) k-mers of the direction in ascending order,
-// idx[] their indices in the caller's order.  Members that end up in a family are flagged in taken[].
-void fam_plan_direction(const uint64_t *v, const uint32_t *idx, size_t n, int k, bool reverse, float alive, FamPlan &out,
-                        std::vector<uint8_t> &taken) {
-    const int root = k / 2 - 2;               // a family shares this many leading bases
-    const int a_min = k - fam_pub(k);          // shallowest trunk row a unit can attach below
-    const int m = bs_check_row_host(k);
-    const size_t kMinMembers = 12;
-    const float single = alive * (float)k + (1.f - alive) * (float)std::min(m, k); // one k-mer scanned on its own
-    const float leftover = 0.5f * single; // a member left to the unit kernels still shares rows there
-    const int cap_rows = fam_state_rows(k);
-    int shape_top[kFamShapes], shape_deep[kFamShapes];
-    float shape_cost[kFamShapes];
-    bool shape_ok[kFamShapes];
-    for (int s = 0; s < kFamShapes; s++) {
-        shape_ok[s] = fam_shape_valid(k, s);
-        fam_unit_rows(k, s, shape_top[s], shape_deep[s]);
-        // + what parking the state costs (6 LDS/STS per row and column block) and the dispatch of a unit
-        shape_cost[s] = (float)shape_top[s] + alive * (float)shape_deep[s] + 0.15f * (float)(shape_top[s] + shape_deep[s]) + 1.0f;
-    }
-    std::vector<uint64_t> mem;
-    std::vector<uint32_t> mem_idx;
-    std::vector<int> lcp_trunk;
-    std::vector<float> f;
-    std::vector<FamUnitPlan> choice, units;
-    for (size_t lo = 0; lo < n;) {
-        size_t hi = lo + 1;
-        while (hi < n && bs_lcp(v[lo], v[hi], k) >= root) hi++;
-        const size_t fam_lo = lo, fam_hi = hi;
-        lo = hi;
-        if (fam_hi - fam_lo < kMinMembers) continue;
-        // trunk = the member on the heavy path: at every depth follow the base most members continue with
-        size_t tl = fam_lo, th = fam_hi;
-        for (int d = root; d < k && th - tl > 1; d++) {
-            const int sh = 2 * (k - 1 - d);
-            size_t best_lo = tl, best_hi = tl, i = tl;
-            while (i < th) {
-                const uint64_t b = (v[i] >> sh) & 3u;
-                size_t j = i + 1;
-                while (j < th && ((v[j] >> sh) & 3u) == b) j++;
-                if (j - i > best_hi - best_lo) { best_lo = i; best_hi = j; }
-                i = j;
-            }
-            tl = best_lo;
-            th = best_hi;
-        }
-        const size_t trunk_at = tl;
-        const uint64_t trunk = v[trunk_at];
-        mem.clear();
-        mem_idx.clear();
-        lcp_trunk.clear();
-        for (size_t i = fam_lo; i < fam_hi; i++) {
-            if (i == trunk_at) continue;
-            mem.push_back(v[i]);
-            mem_idx.push_back(idx[i]);
-            lcp_trunk.push_back(std::min(bs_lcp(v[i], trunk, k), k - 1)); // a copy of the trunk attaches to its last row
-        }
-        // cheapest cover of the members (ascending order) by units and leftovers
-        const size_t nm = mem.size();
-        f.assign(nm + 1, 0.f);
-        choice.assign(nm + 1, FamUnitPlan{0, 0, -1, 0.f});
-        for (size_t i = 1; i <= nm; i++) {
-            f[i] = f[i - 1] + leftover;
-            choice[i] = FamUnitPlan{(uint32_t)(i - 1), 1, -1, leftover};
-            for (int s = 0; s < kFamShapes; s++) {
-                if (!shape_ok[s]) continue;
-                const FamShape sh = fam_shape(s);
-                const int a = k - sh.t - sh.st, p = k - sh.t;
-                if (a < a_min || lcp_trunk[i - 1] < a) continue;
-                // the longest run ending at member i-1 whose members share p bases with each other and a with the trunk
-                size_t g = 1;
-                while (g < (size_t)sh.g && g < i && lcp_trunk[i - 1 - g] >= a && bs_lcp(mem[i - 1 - g], mem[i - 1], k) >= p) g++;
-                const float c = f[i - g] + shape_cost[s];
-                if (c < f[i]) {
-                    f[i] = c;
-                    choice[i] = FamUnitPlan{(uint32_t)(i - g), (uint32_t)g, s, shape_cost[s]};
-                }
-            }
-        }
-        units.clear();
-        for (size_t i = nm; i > 0;) {
-            const FamUnitPlan u = choice[i];
-            if (u.shape >= 0) units.push_back(u);
-            i -= u.count;
-        }
-        int total_rows = 0;
-        for (const FamUnitPlan &u : units) total_rows += shape_top[u.shape] + shape_deep[u.shape];
-        // a CTA needs enough rows to keep its seven consumer warps busy
-        if (units.size() < 4 || total_rows < 100) continue;
-        // passes: as few as the parking area allows, units dealt out heaviest first
-        const int n_pass = (total_rows + cap_rows - 49) / (cap_rows - 48);
-        std::sort(units.begin(), units.end(), [](const FamUnitPlan &x, const FamUnitPlan &y) { return x.cost > y.cost; });
-        std::vector<std::vector<FamUnitPlan>> pass_units((size_t)n_pass);
-        std::vector<int> pass_rows((size_t)n_pass, 0);
-        for (const FamUnitPlan &u : units) { // to the pass with the fewest rows so far
-            const size_t best = (size_t)(std::min_element(pass_rows.begin(), pass_rows.end()) - pass_rows.begin());
-            pass_units[best].push_back(u);
-            pass_rows[best] += shape_top[u.shape] + shape_deep[u.shape];
-        }
-        taken[idx[trunk_at]] = 1;
-        out.n_members++;
-        for (size_t pi = 0; pi < pass_units.size(); pi++) {
-            if (pass_units[pi].empty()) continue;
-            FamPass pass{};
-            pass.trunk = trunk;
-            // the trunk's hits are counted by the family's first pass only
-            pass.trunk_perm = (pi == 0 ? idx[trunk_at] : 0x7FFFFFFFu) | (reverse ? 0x80000000u : 0u);
-            pass.unit_first = (uint32_t)out.units.size();
-            // units to consumers: heaviest first to the least loaded warp
-            float load[7] = {0, 0, 0, 0, 0, 0, 0};
-            std::vector<std::vector<FamUnitPlan>> warp_units(7);
-            for (const FamUnitPlan &u : pass_units[pi]) {
-                int w = 0;
-                for (int j = 1; j < 7; j++)
-                    if (load[j] < load[w]) w = j;
-                load[w] += u.cost;
-                warp_units[(size_t)w].push_back(u);
-            }
-            uint32_t state_row = 0, n_in_pass = 0;
-            for (int w = 0; w < 7; w++) {
-                for (const FamUnitPlan &u : warp_units[(size_t)w]) {
-                    const FamShape sh = fam_shape(u.shape);
-                    FamUnit fu{};
-                    fu.first_kmer = (uint32_t)out.kmers.size();
-                    fu.shape = (uint16_t)u.shape;
-                    fu.state_row = (uint16_t)state_row;
-                    state_row += (uint32_t)(sh.st + sh.g * sh.t);
-                    for (int g = 0; g < sh.g; g++) { // tails past the unit's members repeat the last member and count nothing
-                        const size_t j = u.first + std::min<uint32_t>((uint32_t)g, u.count - 1);
-                        out.kmers.push_back(mem[j]);
-                        out.perm.push_back((uint32_t)g < u.count ? mem_idx[j] : 0xFFFFFFFFu);
-                        if ((uint32_t)g < u.count) {
-                            taken[mem_idx[j]] = 1;
-                            out.n_members++;
-                        }
-                    }
-                    out.units.push_back(fu);
-                    n_in_pass++;
-                    out.lop3_top_per_col += 5.0 * shape_top[u.shape];
-                    out.lop3_all_per_col += 5.0 * (shape_top[u.shape] + shape_deep[u.shape]);
-                }
-                pass.warp_end[w] = n_in_pass;
-            }
-            out.lop3_top_per_col += 5.0 * k - 7.0; // the producer computes every trunk row in every column
-            out.lop3_all_per_col += 5.0 * k - 7.0;
-            out.passes.push_back(pass);
-        }
-    }
-}
-
-} // namespace
-
 // Groups the query k-mers into units.  Each k-mer is looked at forwards and reversed (suffix sharing);
 // a first cover of ALL k-mers in either direction tells which direction serves a k-mer better, then
 // each direction's k-mers are covered on their own (bs_cover).  order[] receives the k-mer indices in scan order
@@ -371,13 +195,11 @@ void fam_plan_direction(const uint64_t *v, const uint32_t *idx, size_t n, int k,
 // stored reversed, units[s] the number of units of shape s.  shape_mask: the shapes that may be used;
 // alive: the expected share of text columns in which a unit's deep rows are computed (bs_unit_cost).
 void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_mask, float alive,
-                      std::vector<uint32_t> &order, std::vector<uint8_t> &reversed, uint32_t (&units)[kBsShapes],
-                      FamPlan *families) {
+                      std::vector<uint32_t> &order, std::vector<uint8_t> &reversed, uint32_t (&units)[kBsShapes]) {
     order.resize(n);
     std::iota(order.begin(), order.end(), 0u);
     reversed.assign(n, 0);
     for (auto &u : units) u = 0;
-    if (families) *families = FamPlan{};
     if (!shape_mask || k < 3 || n < 2) return;
     const BsShapeSet ss(k, shape_mask, alive);
     if (ss.n == 0) return;
@@ -402,12 +224,10 @@ void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_m
         }
     }
 
-    // each k-mer goes to the direction in which it was cheaper, then each direction is covered on its own:
-    // first by families (one CTA per family and 1024 reads, family_core.cuh), the rest by one-warp units
+    // each k-mer goes to the direction in which it was cheaper, then each direction is covered on its own
     std::vector<uint64_t> sv[2];
     std::vector<uint32_t> si[2];
     std::vector<BsGroup> sg[2];
-    std::vector<uint8_t> taken(n, 0);
     for (int d = 0; d < 2; d++) {
         sv[d].reserve(n);
         si[d].reserve(n);
@@ -418,24 +238,8 @@ void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_m
                 si[d].push_back(q);
             }
         }
-        if (families && k >= kFamMinK) {
-            fam_plan_direction(sv[d].data(), si[d].data(), sv[d].size(), k, d != 0, alive, *families, taken);
-            size_t w = 0;
-            for (size_t i = 0; i < sv[d].size(); i++)
-                if (!taken[si[d][i]]) {
-                    sv[d][w] = sv[d][i];
-                    si[d][w] = si[d][i];
-                    w++;
-                }
-            sv[d].resize(w);
-            si[d].resize(w);
-        }
         bs_cover(sv[d].data(), sv[d].size(), ss, f, choice, sg[d]);
     }
-    // the unit kernels see only the k-mers no family took
-    const uint32_t n_rest = (uint32_t)(sv[0].size() + sv[1].size());
-    order.resize(n_rest);
-    reversed.assign(n_rest, 0);
 
     // scan order: shape by shape, forward units then backward units, then the singles (stored forwards)
     uint32_t at = 0;

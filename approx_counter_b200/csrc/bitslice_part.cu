@@ -1,7 +1,6 @@
 // bitslice_part.cu — instantiates the bit-sliced scan kernels for the k with k mod 4 == APC_BS_PART
 // (compiled four times by the Makefile so that the objects build in parallel).
 #include "bitslice_core.cuh"
-#include "family_core.cuh"
 
 #ifndef APC_BS_PART
 #error "compile with -DAPC_BS_PART=0..3"

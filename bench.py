@@ -542,8 +542,6 @@ def run_b200(args, w):
         options.append(("tiles_per_job", args.sg_per_job))
     if args.no_graph:
         options.append(("scan_graph", 0))
-    if args.no_family:
-        options.append(("family", 0))
 
     # ---- this rank's shard of the synthetic read stream, in pinned host memory
     if args.scaling == "strong":  # one job of n reads split over the ranks (contiguous blocks of 32-read tiles)
@@ -807,7 +805,6 @@ def main():
                     help="planner knob (apc_set_option plan_alive_pct): expected share of columns with live deep rows")
     ap.add_argument("--sg-per-job", type=int, default=0,
                     help="tuning knob (apc_set_option tiles_per_job): 1024-read super-groups per job, 0 = auto")
-    ap.add_argument("--no-family", action="store_true", help="one-warp units only (apc_set_option family 0)")
     ap.add_argument("--no-graph", action="store_true", help="launch every scan directly (apc_set_option scan_graph 0)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample size, seconds of CPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")

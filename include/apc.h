@@ -204,8 +204,6 @@ uint64_t apc_last_scan_launches(const apc_ctx *ctx);
  * apc_plan_queries; default all, 0 = one k-mer per warp) and "plan_alive_pct":
  * the share of text columns (percent) in which the planner expects a unit's
  * deep rows to be computed; both applied at the next apc_set_queries.
- * "family": 1 (default) = k-mer families are scanned by the family kernel, 0 =
- * one-warp units only.
  * "scan_graph": 1 (default) = a scan that is issued again unchanged is captured
  * in a CUDA graph and replayed from then on (one launch instead of up to 13 +
  * fork/join events), 0 = always launch directly. */
@@ -226,17 +224,6 @@ int apc_plan_queries(uint8_t k, const uint64_t *kmers, uint32_t n_kmers,
                      uint32_t *order_out, uint8_t *reversed_out,
                      uint32_t *units_out, int32_t *shape_t_out,
                      int32_t *shape_g_out);
-
-/* How apc_set_queries would split these k-mers between the two forms of the
- * default kernel (needs no GPU): k-mers that share their first bases (in
- * either direction) with many others form FAMILIES — one CTA scans a family's
- * trunk once per 1024 reads and the other members branch off it
- * (family_core.cuh) —, the rest goes to the one-warp units of
- * apc_plan_queries.  n_family_kmers + n_unit_kmers == n_kmers; any output
- * pointer may be NULL. */
-int apc_plan_summary(uint8_t k, const uint64_t *kmers, uint32_t n_kmers,
-                     uint32_t *n_family_passes, uint32_t *n_family_units,
-                     uint32_t *n_family_kmers, uint32_t *n_unit_kmers);
 
 /* Integer-pipe peak microbenchmark (roofline denominator):
  * runs dependent-free LOP3 / IMAD / mixed chains on every SM and returns
