@@ -363,8 +363,16 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
         // index of each in the caller's order; bit 31 marks the members of a unit that is scanned backwards
         std::vector<uint32_t> order;
         std::vector<uint8_t> reversed;
-        apc::bs_group_queries(kmers, n_kmers, k, variant.pairing() ? c->opt_shape_mask : 0u, (float)c->opt_alive_pct / 100.f,
-                              order, reversed, units);
+        uint32_t shape_mask = variant.pairing() ? c->opt_shape_mask : 0u;
+        // A small sample is bound by parallelism, not by throughput: a job is one unit x 1024 reads walked column by
+        // column, and with fewer jobs than resident warps the scan takes as long as its longest jobs.  Then only the
+        // shapes of at most 31 rows are used (tools/c1_probe.py on C1, 10 000 reads x 500 k-mers: 0.156 -> 0.105 ms
+        // per step; with all shapes excluded 0.164).
+        if (c->has_sample && shape_mask == 0xFFFFFFFFu) {
+            const uint64_t n_sg = ((uint64_t)c->n_tiles + 31) / 32;
+            if (n_sg * n_kmers / 6 < 2ull * (uint64_t)c->sm_count * 8) shape_mask = apc::kBsSmallShapes;
+        }
+        apc::bs_group_queries(kmers, n_kmers, k, shape_mask, (float)c->opt_alive_pct / 100.f, order, reversed, units);
         uint64_t *hk = (uint64_t *)c->h_pinned;
         uint32_t *hp = (uint32_t *)(hk + n_kmers);
         for (uint32_t i = 0; i < n_kmers; i++) {

@@ -39,6 +39,7 @@ struct BsShape {
 constexpr int kBsShapes = 12;
 constexpr int kBsMaxRows = 48;
 constexpr int kBsAlivePct = 30;
+constexpr uint32_t kBsSmallShapes = 0xFC0u; // shapes 6..11 of bs_shape: units of at most 31 rows (small samples)
 constexpr BsShape bs_shape(int k, int s) {
     const BsShape table[kBsShapes] = {{2, 16}, {6, 6}, {5, 6}, {8, 4}, {2, 12}, {3, 8}, {6, 3}, {2, 8}, {3, 6}, {3, 4}, {1, 4}, {k - k / 2, 2}};
     const BsShape sh = table[s];
@@ -59,12 +60,8 @@ constexpr int bs_check_row_host(int k) {
     return k >= 18 ? 14 : k >= 16 ? 13 : k;
 #endif
 }
-// Column pairs of the bit planes a scan kernel keeps in flight ahead of the pair it computes (A/B builds:
-// -DAPC_BS_PREFETCH_PAIRS=2 or 3); the plane buffer is padded by that many columns at either end.
-#ifndef APC_BS_PREFETCH_PAIRS
-#define APC_BS_PREFETCH_PAIRS 1
-#endif
-constexpr int kBsPadCols = 2 * APC_BS_PREFETCH_PAIRS;
+// The scan kernels prefetch one column pair past either end of a read: the plane buffer is padded by that much.
+constexpr int kBsPadCols = 2;
 struct BsRange { // super-groups (1024 reads) and reads [lo, hi) of one scan
     uint32_t sg_first, n_sg;
     uint64_t lo, hi;
@@ -158,7 +155,7 @@ struct Ctx {
     cudaStream_t graph_stream = nullptr, last_scan_stream = nullptr;
     uint64_t graph_launches = 0;
     double graph_lop3[3] = {0., 0., 0.}; // the plan statistics of one replay (top, all, one k-mer per warp)
-    int opt_graph = 1; // 0 = never capture
+    int opt_graph = 0; // 1 = a repeated scan is captured and replayed (apc_set_option "scan_graph")
 
     // multi-GPU: an NCCL communicator (one rank per context), libnccl loaded on first use (apc_comm.cpp)
     void *nccl_comm = nullptr;

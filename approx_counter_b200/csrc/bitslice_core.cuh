@@ -115,7 +115,9 @@ __device__ __forceinline__ uint32_t bs_valid_mask(uint64_t first, uint64_t range
     return vm;
 }
 
-// job fetch of the persistent warps: warp-uniform result (ptxas keeps it in uniform registers)
+// job fetch of the persistent warps: warp-uniform result (ptxas keeps it in uniform registers).  Claiming one job
+// ahead (the atomic's round trip hidden behind the job) was measured and is not worth its lines: C2 372.9 vs 375.3,
+// C3 674.7 vs 671.0, C4 651.5 vs 654.6 kGCUPS with / without (tools/ab_bench.sh).
 __device__ __forceinline__ uint32_t bs_next_job(unsigned int *job_counter, uint32_t n_jobs, uint32_t lane) {
     uint32_t job = 0;
     if (lane == 0) {
@@ -140,31 +142,22 @@ static __device__ unsigned long long g_bs_stats[2];
 #define APC_BS_STAT(run_) do { } while (0)
 #endif
 
-// Plane prefetch: the column pair after the one being computed is always in registers (na, nb); deeper
-// builds (APC_BS_PREFETCH_PAIRS = D > 1) keep D - 1 more pairs in flight in qa[], qb[].
-#if APC_BS_PREFETCH_PAIRS == 1
-#define APC_BS_PREFETCH_INIT(p_, step_)
-#define APC_BS_PREFETCH_NEXT(p_, step_) const uint4 na = __ldg(p_), nb = __ldg((p_) + (step_));
-#else
-#define APC_BS_PREFETCH_INIT(p_, step_)                                                          \
-    uint4 qa[APC_BS_PREFETCH_PAIRS], qb[APC_BS_PREFETCH_PAIRS];                                  \
-    _Pragma("unroll") for (int d_ = 0; d_ < APC_BS_PREFETCH_PAIRS; d_++) {                       \
-        qa[d_] = __ldg((p_) + (2 * (d_ + 1)) * (step_));                                         \
-        qb[d_] = __ldg((p_) + (2 * (d_ + 1) + 1) * (step_));                                     \
-    }
-#define APC_BS_PREFETCH_NEXT(p_, step_)                                                          \
-    const uint4 na = qa[0], nb = qb[0];                                                          \
-    _Pragma("unroll") for (int d_ = 0; d_ + 1 < APC_BS_PREFETCH_PAIRS; d_++) {                   \
-        qa[d_] = qa[d_ + 1];                                                                     \
-        qb[d_] = qb[d_ + 1];                                                                     \
-    }                                                                                            \
-    qa[APC_BS_PREFETCH_PAIRS - 1] = __ldg((p_) + (2 * APC_BS_PREFETCH_PAIRS) * (step_));         \
-    qb[APC_BS_PREFETCH_PAIRS - 1] = __ldg((p_) + (2 * APC_BS_PREFETCH_PAIRS + 1) * (step_));
-#endif
-
+// Plane prefetch: the masks of a column pair are dead once they are parked in the warp's shared-memory slot, so the
+// next pair is loaded into the same registers right after the staging — one pair of prefetch distance (two pairs in
+// flight were measured in round 1 and again in round 2: slower), no second set of registers, no moves.
 #define APC_BS_STAGE_MASKS()                                                                                          \
     s_mask[0][lane] = ma.x; s_mask[0][32 + lane] = ma.y; s_mask[0][64 + lane] = ma.z; s_mask[0][96 + lane] = ma.w;   \
     s_mask[1][lane] = mb.x; s_mask[1][32 + lane] = mb.y; s_mask[1][64 + lane] = mb.z; s_mask[1][96 + lane] = mb.w;
+
+// The column-pair loops are unrolled twice for k >= 18: the second copy writes the plane double buffer back into the
+// registers the first read it from, which removes ~19 register moves per pair (A/B on B200, tools/ab_bench.sh:
+// C3, k = 20: 646 -> 675 kGCUPS; C2, k = 16: 373 -> 364, the doubled loop body costs more than the moves there).
+// -DAPC_BS_PAIR_UNROLL=n forces n for every k (A/B builds).
+#ifdef APC_BS_PAIR_UNROLL
+__host__ __device__ constexpr int bs_pair_unroll(int) { return APC_BS_PAIR_UNROLL; }
+#else
+__host__ __device__ constexpr int bs_pair_unroll(int k) { return k >= 18 ? 2 : 1; }
+#endif
 
 // One k-mer per warp.  kmers[u] is the k-mer of unit u, perm[u] its index in the caller's order.
 template <int K, int MB, int M = bs_check_row(K)>
@@ -196,11 +189,12 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
             bool deep_zero = true; // rows M..K-2 are all zero (they start that way)
             const uint4 *p = planes + ((size_t)(sg_first + sg) * cols) * kGroupsPerSuper + lane;
             uint4 ma = __ldg(p), mb = __ldg(p + kGroupsPerSuper);
-            APC_BS_PREFETCH_INIT(p, kGroupsPerSuper)
+#pragma unroll(bs_pair_unroll(K))
             for (uint32_t pr = 0; pr < pairs; pr++) {
-                p += 2 * kGroupsPerSuper;
-                APC_BS_PREFETCH_NEXT(p, kGroupsPerSuper) // defines na, nb; the buffer is padded by kBsPadCols columns
                 APC_BS_STAGE_MASKS()
+                p += 2 * kGroupsPerSuper; // the buffer is padded by kBsPadCols columns
+                ma = __ldg(p);
+                mb = __ldg(p + kGroupsPerSuper);
                 const char *slot_a = reinterpret_cast<const char *>(s_mask[0]) + lane * 4;
                 const char *slot_b = reinterpret_cast<const char *>(s_mask[1]) + lane * 4;
                 if constexpr (M >= K) {
@@ -232,7 +226,6 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
                         bs_rows<K, 0, true, M, K>(r0, r1, r2, cb, slot_b, off);
                     }
                 }
-                ma = na; mb = nb;
             }
             // hits of these 32 reads: [d<=0] + [d<=1] + [d<=2] (:589-593) = the sticky row k-1; reads outside
             // the scanned range (padding of the last group, or a sub-range scan) masked out
@@ -302,11 +295,12 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
             bool deep_zero = true; // the deep rows other than the hit rows are all zero (they start that way)
             const uint4 *p = planes + ((size_t)(sg_first + sg) * cols + col0) * kGroupsPerSuper + lane;
             uint4 ma = __ldg(p), mb = __ldg(p + cstep);
-            APC_BS_PREFETCH_INIT(p, cstep)
+#pragma unroll(bs_pair_unroll(K))
             for (uint32_t pr = 0; pr < pairs; pr++) {
-                p += 2 * cstep;
-                APC_BS_PREFETCH_NEXT(p, cstep) // defines na, nb; the buffer is padded by kBsPadCols columns at both ends
                 APC_BS_STAGE_MASKS()
+                p += 2 * cstep; // the buffer is padded by kBsPadCols columns at both ends
+                ma = __ldg(p);
+                mb = __ldg(p + cstep);
                 if constexpr (M < K && M <= P) {
                     // top = trunk rows 0..M-1; deep = the rest of the trunk and the tails.  The top rows of both
                     // columns first (they do not depend on the deep rows), then one test per column pair.
@@ -391,7 +385,6 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                     }
                 }
                 }
-                ma = na; mb = nb;
             }
             const uint32_t vm = bs_valid_mask(((uint64_t)(sg_first + sg) * kGroupsPerSuper + lane) * 32, range_lo, range_hi);
 #pragma unroll

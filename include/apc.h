@@ -204,9 +204,11 @@ uint64_t apc_last_scan_launches(const apc_ctx *ctx);
  * apc_plan_queries; default all, 0 = one k-mer per warp) and "plan_alive_pct":
  * the share of text columns (percent) in which the planner expects a unit's
  * deep rows to be computed; both applied at the next apc_set_queries.
- * "scan_graph": 1 (default) = a scan that is issued again unchanged is captured
- * in a CUDA graph and replayed from then on (one launch instead of up to 13 +
- * fork/join events), 0 = always launch directly. */
+ * "scan_graph": 1 = a scan that is issued again unchanged is captured in a CUDA
+ * graph and replayed from then on (one launch instead of up to 13 + fork/join
+ * events), 0 (default) = always launch directly — back-to-back scans hide the
+ * launches behind the previous scan anyway, and the graph's node dependencies
+ * cost about what it saves (DESIGN.md tuning log). */
 int apc_set_option(apc_ctx *ctx, const char *name, int64_t value);
 
 /* The scan plan apc_set_queries would build for these k-mers (needs no GPU):
