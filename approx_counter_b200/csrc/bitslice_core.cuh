@@ -175,6 +175,9 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
         const uint32_t job = bs_next_job(job_counter, n_jobs, lane);
         if (job >= n_jobs) break;
         const uint32_t u = job % n_units, jb = job / n_units;
+        // the first column pair of the job is requested before the row offsets are computed
+        const uint4 *p = planes + ((size_t)(sg_first + jb * sg_per_job) * cols) * kGroupsPerSuper + lane;
+        uint4 ma = __ldg(p), mb = __ldg(p + kGroupsPerSuper);
         const uint64_t kmer = __ldg(kmers + u);
         uint32_t off[K]; // byte offset of the mask row (A, C, G, T) that k-mer base i selects
 #pragma unroll
@@ -187,8 +190,6 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
             uint32_t r0[K], r1[K], r2[K];
             bs_rows_init<K, 0>(r0, r1, r2);
             bool deep_zero = true; // rows M..K-2 are all zero (they start that way)
-            const uint4 *p = planes + ((size_t)(sg_first + sg) * cols) * kGroupsPerSuper + lane;
-            uint4 ma = __ldg(p), mb = __ldg(p + kGroupsPerSuper);
 #pragma unroll(bs_pair_unroll(K))
             for (uint32_t pr = 0; pr < pairs; pr++) {
                 APC_BS_STAGE_MASKS()
@@ -226,6 +227,11 @@ bs_scan_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const 
                         bs_rows<K, 0, true, M, K>(r0, r1, r2, cb, slot_b, off);
                     }
                 }
+            }
+            if (sg + 1 < sg_end) { // the next 1024 reads' first column pair, before the epilogue of these
+                p = planes + ((size_t)(sg_first + sg + 1) * cols) * kGroupsPerSuper + lane;
+                ma = __ldg(p);
+                mb = __ldg(p + kGroupsPerSuper);
             }
             // hits of these 32 reads: [d<=0] + [d<=1] + [d<=2] (:589-593) = the sticky row k-1; reads outside
             // the scanned range (padding of the last group, or a sub-range scan) masked out
@@ -266,6 +272,14 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
         const uint32_t job = bs_next_job(job_counter, n_jobs, lane);
         if (job >= n_jobs) break;
         const uint32_t u = job % n_units, jb = job / n_units;
+        // direction of the walk: first column and the (signed) distance between consecutive columns
+        const bool reverse = (__ldg(perm + (size_t)G * u) >> 31) != 0;
+        const int64_t cstep = reverse ? -(int64_t)kGroupsPerSuper : (int64_t)kGroupsPerSuper;
+        const size_t col0 = reverse ? 2 * (size_t)pairs - 1 : 0;
+        // the first column pair of the job is requested before anything else: the row offsets below are computed
+        // while it travels (the prologue of a job used to stall on these loads)
+        const uint4 *p = planes + ((size_t)(sg_first + jb * sg_per_job) * cols + col0) * kGroupsPerSuper + lane;
+        uint4 ma = __ldg(p), mb = __ldg(p + cstep);
         uint32_t off_s[P], off_t[G][T];
         {
             const uint64_t k0 = __ldg(kmers + (size_t)G * u);
@@ -278,10 +292,6 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
 #pragma unroll
             for (int i = 0; i < T; i++) off_t[g][i] = (uint32_t)((kg >> (2 * (T - 1 - i))) & 3u) * kPlaneRow;
         }
-        // direction of the walk: first column and the (signed) distance between consecutive columns
-        const bool reverse = (__ldg(perm + (size_t)G * u) >> 31) != 0;
-        const int64_t cstep = reverse ? -(int64_t)kGroupsPerSuper : (int64_t)kGroupsPerSuper;
-        const size_t col0 = reverse ? 2 * (size_t)pairs - 1 : 0;
         uint32_t cnt[G];
 #pragma unroll
         for (int g = 0; g < G; g++) cnt[g] = 0;
@@ -293,8 +303,6 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
 #pragma unroll
             for (int g = 0; g < G; g++) bs_rows_init<T, P>(x0[g], x1[g], x2[g]);
             bool deep_zero = true; // the deep rows other than the hit rows are all zero (they start that way)
-            const uint4 *p = planes + ((size_t)(sg_first + sg) * cols + col0) * kGroupsPerSuper + lane;
-            uint4 ma = __ldg(p), mb = __ldg(p + cstep);
 #pragma unroll(bs_pair_unroll(K))
             for (uint32_t pr = 0; pr < pairs; pr++) {
                 APC_BS_STAGE_MASKS()
@@ -385,6 +393,11 @@ bs_group_kernel(const uint4 *__restrict__ planes, const uint32_t sg_first, const
                     }
                 }
                 }
+            }
+            if (sg + 1 < sg_end) { // the next 1024 reads' first column pair, before the epilogue of these
+                p = planes + ((size_t)(sg_first + sg + 1) * cols + col0) * kGroupsPerSuper + lane;
+                ma = __ldg(p);
+                mb = __ldg(p + cstep);
             }
             const uint32_t vm = bs_valid_mask(((uint64_t)(sg_first + sg) * kGroupsPerSuper + lane) * 32, range_lo, range_hi);
 #pragma unroll
