@@ -42,6 +42,7 @@ SYMBOLS = {
     "apc_last_error": (C.c_char_p, [_vp]),
     "apc_set_stream": (C.c_int, [_vp, _vp]),
     "apc_sync": (C.c_int, [_vp]),
+    "apc_reserve": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_uint8, C.c_uint32]),
     "apc_upload_sample": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32]),
     "apc_upload_sample_async": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32]),
     "apc_upload_sample_ragged": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),

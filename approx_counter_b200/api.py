@@ -70,6 +70,10 @@ class ApproxCounter:
     def set_option(self, name, value):
         self._check(self._lib.apc_set_option(self._h, name.encode(), int(value)))
 
+    def reserve(self, n_reads, read_len, k, n_kmers=0):
+        """One-time set-up for one-shot hosts (apc_reserve): buffers allocated, kernels loaded."""
+        self._check(self._lib.apc_reserve(self._h, int(n_reads), int(read_len), int(k), int(n_kmers)))
+
     # -- sample -------------------------------------------------------------------
     def upload_sample(self, sample):
         """sample: uint8[n, L] ASCII matrix (uniform length), or a list of

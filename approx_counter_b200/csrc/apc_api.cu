@@ -270,6 +270,53 @@ int apc_upload_sample_ragged(apc_ctx *c, const uint8_t *bases, const uint64_t *o
     APC_CATCH(c)
 }
 
+int apc_reserve(apc_ctx *c, uint64_t n_reads, uint32_t read_len, uint8_t k, uint32_t n_kmers) {
+    APC_TRY
+    int st = apc::bind(c);
+    if (st) return st;
+    if (k < 2 || k > 32) return apc::fail(c, APC_ERR_INVALID, "k must be in [2,32]");
+    // the buffers of the expected sample and of the exact stage's k-windows
+    if ((st = apc::prepare_sample(c, n_reads, read_len, n_reads * read_len))) return st;
+    if ((st = apc::grow(c, c->d_stage, c->stage_cap, (size_t)n_reads * read_len))) return st;
+    const uint64_t windows = read_len >= k ? n_reads * (uint64_t)(read_len - k + 1) : 0;
+    if ((st = apc::exact_reserve(c, k, windows))) return st;
+    // the whole path once on a 64-read dummy sample: loads the layout kernels, the exact stage (the library sort
+    // included) and the scan kernels the dummy's plan uses; then every other scan kernel of this k
+    {
+        const uint32_t len = std::max<uint32_t>(read_len, (uint32_t)k + 8u);
+        std::vector<uint8_t> dummy((size_t)64 * len);
+        uint32_t x = 12345u;
+        for (auto &b : dummy) {
+            x = x * 1664525u + 1013904223u;
+            b = (uint8_t)"ACGT"[x >> 30];
+        }
+        for (uint32_t r = 0; r < 64; r += 2)
+            std::memcpy(&dummy[(size_t)r * len], &dummy[0], k + 4u); // a shared prefix: something to group
+        if ((st = apc_upload_sample(c, dummy.data(), 64, len))) return st;
+        const uint32_t lim = std::max<uint32_t>(16u, std::min<uint32_t>(n_kmers, 64u));
+        std::vector<uint64_t> km(lim), ct(lim);
+        uint64_t n_top = 0;
+        if ((st = apc_exact_topn(c, k, 1e30f, lim, nullptr, 0, km.data(), ct.data(), &n_top, nullptr, nullptr))) return st;
+        if (n_top && (st = apc_approx_count(c, k, km.data(), (uint32_t)n_top, ct.data()))) return st;
+    }
+    APC_CUDA(c, apc::warm_bs_kernels(*c, k));
+    if (n_kmers) { // the query tables and the count vector
+        const size_t words = (size_t)n_kmers * 3;
+        if ((st = apc::grow(c, c->d_kmers, c->kmers_cap, words * sizeof(uint32_t)))) return st;
+        if ((st = apc::grow(c, c->d_counts, c->counts_cap, (size_t)n_kmers * sizeof(unsigned long long)))) return st;
+    }
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->has_sample = false; // the dummy is not a sample anyone asked for
+    c->k = 0;
+    c->plan_gen++;
+    c->timing = apc_timing{};
+    c->stat_scans = 0;
+    c->stat_lop3_top = c->stat_lop3_all = c->stat_lop3_single = 0.;
+    APC_CUDA(c, cudaMemsetAsync(c->d_deep_lop3, 0, sizeof(unsigned long long), c->stream));
+    return APC_OK;
+    APC_CATCH(c)
+}
+
 int apc_sample_info(const apc_ctx *c, uint64_t *n_reads, uint32_t *max_len, uint64_t *total_bases) {
     if (!c) return APC_ERR_INVALID;
     if (n_reads) *n_reads = c->n_reads;

@@ -216,6 +216,7 @@ cudaError_t launch_bs_scan(const Ctx &c, uint64_t read_lo, uint64_t read_hi, uns
 void bs_group_queries(const uint64_t *kmers, uint32_t n, int k, uint32_t shape_mask, float alive,
                       std::vector<uint32_t> &order, std::vector<uint8_t> &reversed, uint32_t (&units)[kBsShapes]);
 uint64_t bs_reverse_kmer(uint64_t kmer, int k);
+cudaError_t warm_bs_kernels(const Ctx &c, int k);
 
 // exact_kernels.cu
 int exact_count_select(Ctx *c, uint8_t k, float lc_adjusted, uint64_t lim, uint64_t solid_km,
@@ -223,6 +224,7 @@ int exact_count_select(Ctx *c, uint8_t k, float lc_adjusted, uint64_t lim, uint6
                        std::vector<uint64_t> &kmers, std::vector<uint64_t> &counts, uint64_t *n_needed,
                        uint64_t *n_distinct, uint64_t *n_had_n);
 void free_exact_scratch(Ctx *c);
+int exact_reserve(Ctx *c, uint8_t k, uint64_t max_windows);
 
 // peak_kernels.cu
 cudaError_t measure_int_peak(const Ctx &c, double *lop3, double *imad, double *mixed);

@@ -429,6 +429,7 @@ struct BsLaunchCtx {
     int slot; // next stream / job counter
     // LOP3 warp instructions of this scan: in the rows computed in every column, and in all rows if nothing were skipped
     double lop3_top = 0., lop3_all = 0.;
+    bool warm = false; // load every kernel of this k instead of launching (apc_reserve)
 };
 
 inline uint32_t bs_sg_per_job(const BsLaunchCtx &l, uint32_t n_units, int mb) {
@@ -443,6 +444,10 @@ template <typename Kernel>
 static cudaError_t bs_launch_one(BsLaunchCtx &l, Kernel kernel, int mb, uint32_t first_kmer, uint32_t n_units,
                                  const BsRowSplit split) {
     const Ctx &c = *l.c;
+    if (l.warm) { // CUDA loads a kernel at its first launch (lazy loading): asking for its attributes loads it now
+        cudaFuncAttributes attr;
+        return cudaFuncGetAttributes(&attr, kernel);
+    }
     {   // rows 0 and 1 hold constants at levels 1 and 2: 7 LOP3 fewer than 5 per row (bs_rows)
         const double unit_cols = (double)n_units * l.r.n_sg * (2 * ((c.max_len + 1) / 2));
         l.lop3_top += unit_cols * (5 * split.top - 7);
@@ -478,7 +483,7 @@ static cudaError_t bs_launch_shapes(BsLaunchCtx &l, uint32_t &first_kmer) {
         constexpr BsShape sh = bs_shape(K, S);
         if constexpr (sh.g > 0) {
             const uint32_t n_units = l.c->bs_units[S];
-            if (n_units) {
+            if (n_units || l.warm) {
                 constexpr int MB = bs_warps_per_sm_c(K - sh.t + sh.g * sh.t);
                 cudaError_t e = bs_launch_one(l, bs_group_kernel<K, K - sh.t, sh.g, MB>, MB, first_kmer, n_units,
                                               bs_rows_split(K, K - sh.t, sh.g, bs_check_row(K)));
@@ -499,7 +504,7 @@ static cudaError_t launch_bs_k(BsLaunchCtx &l) {
     // shapes in table order (the heaviest units first), then the k-mers that found no partner
     cudaError_t e = bs_launch_shapes<K, 0>(l, first);
     if (e != cudaSuccess) return e;
-    if (first < c.n_kmers) {
+    if (first < c.n_kmers || l.warm) {
         // registers: 3K of state + the row masks of two columns in flight (ptxas wants about 6K + 26);
         // CTAs (= warps) per SM chosen so that nothing spills
         constexpr int MB = bs_warps_per_sm_c(K);

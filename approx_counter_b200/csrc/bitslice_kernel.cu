@@ -274,6 +274,32 @@ cudaError_t launch_bs_part1(BsLaunchCtx &l);
 cudaError_t launch_bs_part2(BsLaunchCtx &l);
 cudaError_t launch_bs_part3(BsLaunchCtx &l);
 
+static cudaError_t bs_dispatch(BsLaunchCtx &l) {
+    switch (l.c->k & 3) { // the instantiations are spread over four objects by k mod 4 (bitslice_part.cu)
+    case 0: return launch_bs_part0(l);
+    case 1: return launch_bs_part1(l);
+    case 2: return launch_bs_part2(l);
+    default: return launch_bs_part3(l);
+    }
+}
+
+// Loads every scan kernel of this k (the twelve unit shapes and the single-k-mer kernel) without launching anything.
+cudaError_t warm_bs_kernels(const Ctx &c, int k) {
+    if (k < 2 || k > 32) return cudaErrorInvalidValue;
+    Ctx tmp = c; // only k is looked at
+    tmp.k = (uint8_t)k;
+    uint64_t launches = 0;
+    BsLaunchCtx l;
+    l.c = &tmp;
+    l.r = BsRange{0, 0, 0, 0};
+    l.d_counts = nullptr;
+    l.sg_per_job_opt = 0;
+    l.launches = &launches;
+    l.slot = 0;
+    l.warm = true;
+    return bs_dispatch(l);
+}
+
 cudaError_t launch_bs_scan(const Ctx &c, uint64_t lo, uint64_t hi, unsigned long long *d_counts, uint32_t sg_per_job,
                            uint64_t *launches) {
     BsLaunchCtx l;
@@ -292,12 +318,7 @@ cudaError_t launch_bs_scan(const Ctx &c, uint64_t lo, uint64_t hi, unsigned long
     // the launches of the shapes run side by side: fork point for the side streams
     cudaError_t e = cudaEventRecord(c.bs_fork, c.stream);
     if (e != cudaSuccess) return e;
-    switch (c.k & 3) { // the instantiations are spread over four objects by k mod 4 (bitslice_part.cu)
-    case 0: e = launch_bs_part0(l); break;
-    case 1: e = launch_bs_part1(l); break;
-    case 2: e = launch_bs_part2(l); break;
-    default: e = launch_bs_part3(l); break;
-    }
+    e = bs_dispatch(l);
     // statistics (apc_scan_stats_read): what this scan costs on the ALU pipe according to its plan
     c.stat_scans++;
     c.stat_lop3_top += l.lop3_top;

@@ -14,7 +14,11 @@ namespace apc {
 cudaError_t APC_BS_CAT(launch_bs_part, APC_BS_PART)(BsLaunchCtx &l) {
     switch (l.c->k) {
 #define APC_BS_CASE(K_) case K_: return launch_bs_k<K_>(l);
-#if APC_BS_PART == 0
+#ifdef APC_BS_ONLY_K // experiment builds: one k only (context creation time against the number of kernels)
+#if (APC_BS_ONLY_K % 4) == APC_BS_PART || (APC_BS_ONLY_K % 4 == 0 && APC_BS_PART == 0)
+        APC_BS_CASE(APC_BS_ONLY_K)
+#endif
+#elif APC_BS_PART == 0
         APC_BS_CASE(4) APC_BS_CASE(8) APC_BS_CASE(12) APC_BS_CASE(16) APC_BS_CASE(20) APC_BS_CASE(24) APC_BS_CASE(28)
         APC_BS_CASE(32)
 #elif APC_BS_PART == 1

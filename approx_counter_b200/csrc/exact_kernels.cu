@@ -703,6 +703,36 @@ int run_exact(Ctx *c, int k, uint32_t lc_min_sum, uint64_t lim, uint64_t solid_k
 
 } // namespace
 
+// Allocates the scratch of the exact stage for up to max_windows k-windows (every window distinct: the upper bound of
+// each buffer), so that the first apc_exact_topn of a one-shot run does not spend its time in cudaMalloc.
+int exact_reserve(Ctx *c, uint8_t k, uint64_t max_windows) {
+    ExactScratch &x = c->exact;
+    if (max_windows == 0) return APC_OK;
+    if (max_windows >= 0xFFFFFFFFull) return fail(c, APC_ERR_INVALID, "exact stage: more than 2^32-2 windows");
+    const size_t kb = k <= 16 ? sizeof(uint32_t) : sizeof(uint64_t);
+    int st;
+    if ((st = grow_dev(c, x.d_counters, x.counters_cap, CNT_SLOTS * sizeof(unsigned long long)))) return st;
+    if ((st = grow_dev(c, x.d_hist, x.hist_cap, 512 * sizeof(unsigned long long)))) return st;
+    if ((st = grow_dev(c, x.d_keys_a, x.keys_a_cap, max_windows * kb))) return st;
+    if ((st = grow_dev(c, x.d_keys_b, x.keys_b_cap, max_windows * kb))) return st;
+    size_t temp_bytes = 0, scan_bytes = 0;
+    const unsigned n_pass_blocks = blocks_for(max_windows, kPassTile);
+    if (k <= 16)
+        APC_CUDA(c, cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                   (unsigned long long)max_windows, 0, 2 * k, c->stream));
+    else
+        APC_CUDA(c, cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                                   (unsigned long long)max_windows, 0, 2 * k, c->stream));
+    APC_CUDA(c, cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                              (int)n_pass_blocks, c->stream));
+    if ((st = grow_dev(c, x.d_temp, x.temp_cap, std::max(temp_bytes, scan_bytes)))) return st;
+    if ((st = grow_dev(c, x.d_block_a, x.block_a_cap, (size_t)n_pass_blocks * sizeof(uint32_t)))) return st;
+    if ((st = grow_dev(c, x.d_block_b, x.block_b_cap, (size_t)n_pass_blocks * sizeof(uint32_t)))) return st;
+    if ((st = grow_dev(c, x.d_start, x.start_cap, (max_windows + 1) * sizeof(uint32_t)))) return st;
+    if ((st = grow_dev(c, x.d_dsum, x.dsum_cap, max_windows * sizeof(uint16_t)))) return st;
+    return APC_OK;
+}
+
 void free_exact_scratch(Ctx *c) {
     ExactScratch &x = c->exact;
     cudaFree(x.d_keys_a);

@@ -261,9 +261,17 @@ int cli_main(int argc, const char **argv) {
     if (n_gpus < 1) n_gpus = 1;
     std::vector<Gpu> gpus(n_gpus);
     int create_status = APC_OK;
+    double create_ms = 0., reserve_ms = 0.;
     std::thread creator([&]() {
+        const auto t0 = std::chrono::steady_clock::now();
         for (uint64_t g = 0; g < n_gpus && create_status == APC_OK; g++)
             create_status = apc_create((int)(device0 + g), &gpus[g].ctx);
+        // buffers for the largest sample this run can draw (sn reads of sl + 1 bases) and every kernel of this k,
+        // while the main thread parses the input; a failure here is not fatal, the calls below allocate on demand
+        create_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (create_status == APC_OK && k <= sl)
+            apc_reserve(gpus[0].ctx, std::min<uint64_t>(sn, 4u << 20), (uint32_t)(sl + 1), (uint8_t)k, (uint32_t)std::min<uint64_t>(limit, 1u << 20));
+        reserve_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() - create_ms;
     });
     struct Joiner { // an exception out of read_fastx (bad_alloc on a huge input) must not leave the thread joinable
         std::thread &t;
@@ -275,7 +283,11 @@ int cli_main(int argc, const char **argv) {
     {
         std::string err;
         const bool parsed = read_fastx(input_file, seqs, err);
+        if (v > 1) print("File parsed; waiting for the CUDA context", tab_level);
         creator.join();
+        if (v > 1)
+            print("CUDA context ready (beside the parsing: context " + std::to_string(create_ms) + " ms, buffers and kernels " +
+                      std::to_string(reserve_ms) + " ms)", tab_level);
         if (create_status != APC_OK) return gpu_fail("cannot open CUDA device", nullptr, create_status);
         if (!parsed) {
             std::cerr << error_pref << err << std::endl;

@@ -71,6 +71,16 @@ const char *apc_last_error(const apc_ctx *ctx);
 int apc_set_stream(apc_ctx *ctx, void *cuda_stream);
 int apc_sync(apc_ctx *ctx);
 
+/* Optional one-time set-up for hosts that run once and exit (the drop-in binary
+ * calls it beside the parsing of its input, :819-825): allocates the device
+ * buffers of a sample of n_reads x read_len, the exact stage's scratch for its
+ * k-windows and the tables of n_kmers queries, and runs the whole path once on
+ * a 64-read dummy sample so that every kernel the real calls launch is loaded
+ * (CUDA loads kernels lazily at their first launch).  Leaves the context
+ * without sample and queries; every other entry point works without it. */
+int apc_reserve(apc_ctx *ctx, uint64_t n_reads, uint32_t read_len, uint8_t k,
+                uint32_t n_kmers);
+
 /* ---- the sampled text ------------------------------------------------------
  * Replaces the `sequence_set_type sample` that sampleSequences returns (:415,
  * :867) and errorCount indexes (:537-541): instead of a SeqAn FM index the

@@ -411,3 +411,26 @@ def test_scan_graph_replay_and_statistics(built):
             part = orc.error_count(codes[: 2048 * 100], offs[:2049], kmers[::-1].copy(), 16, fast=True)
             assert np.array_equal(c.get_counts(), part)
     assert per_scan[0] == per_scan[1]
+
+
+def test_reserve_changes_nothing_but_the_first_call_cost(built):
+    """apc_reserve (buffers pre-sized, kernels loaded on a dummy sample) leaves the context without sample and
+    queries, and every result afterwards is what it is without it."""
+    from approx_counter_b200 import ApcError, ApproxCounter, host
+    sample = np.ascontiguousarray(orc.synth_ends(99, 0, 6000, 100, True))
+    codes, offs = orc.encode_matrix(sample)
+    thr = host.adjust_threshold(1.0, 16, 16)
+    with ApproxCounter(0) as plain, ApproxCounter(0) as warm:
+        warm.reserve(6000, 101, 16, 300)
+        with pytest.raises(ApcError):
+            warm.scan()                                   # no sample, no queries after reserve
+        res = []
+        for c in (plain, warm):
+            c.upload_sample(sample)
+            km, ct, nd, hn = c.count_kmers_topn(16, thr, 300)
+            res.append((km, ct, nd, hn, c.errorCount(km, 16), c.timing()["exact_ms"]))
+        for a, b in zip(res[0][:5], res[1][:5]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(res[1][4], orc.error_count(codes, offs, res[1][0], 16, fast=True))
+        st = warm.scan_stats()
+        assert st["scans"] == 1                           # the dummy run is not in the tally
