@@ -283,11 +283,19 @@ def test_units_of_every_shape_and_direction(counter, k):
         assert (plan["units"] > 0).sum() >= 3 and 0 < plan["reversed"].sum() < len(kmers)
     counter.set_option("scan_variant", 0)
     counter.upload_sample(reads)
-    got = counter.errorCount(kmers, k)
     codes, offs = orc.encode(reads)
     want = orc.error_count(codes, offs, kmers, k, fast=True)
-    assert np.array_equal(got, want)
-    # sub-range of the resident sample (what the multi-GPU binary does)
+    # a sample this small is planned with the small shapes only (kBsSmallShapes); an explicit mask of all twelve
+    # shapes switches that rule off, so both plans are checked
+    try:
+        for mask in (0xFFFFFFFF, 0xFFF):
+            counter.set_option("shape_mask", mask)
+            got = counter.errorCount(kmers, k)
+            assert np.array_equal(got, want), hex(mask)
+    except Exception:
+        counter.set_option("shape_mask", 0xFFFFFFFF)
+        raise
+    # sub-range of the resident sample (what the multi-GPU binary does), with every shape
     lo, hi = 32 * 7, 32 * 7 + 1001
     counter.set_queries(kmers, k)
     try:
@@ -298,6 +306,7 @@ def test_units_of_every_shape_and_direction(counter, k):
     finally:
         counter.set_option("scan_first_read", 0)
         counter.set_option("scan_n_reads", -1)
+        counter.set_option("shape_mask", 0xFFFFFFFF)
     codes, offs = orc.encode(reads[lo:hi])
     assert np.array_equal(part, orc.error_count(codes, offs, kmers, k, fast=True))
 

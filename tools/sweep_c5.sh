@@ -10,6 +10,6 @@ fi
 for pt in $points; do
   n=${pt%%:*}; q=${pt##*:}
   steps=5; [ $((n * q)) -ge 5000000000 ] && steps=2; [ $((n * q)) -ge 100000000000 ] && steps=1
-  python bench.py --workload C2 --reads $n --lim $q --steps $steps --warmup 3 --no-cpu-baseline >> gpurun_out/sweep_c5.jsonl 2>> gpurun_out/sweep_c5.err || echo "{\"failed\": [$n, $q]}" >> gpurun_out/sweep_c5.jsonl
+  python bench.py --workload C2 --reads $n --lim $q --steps $steps --warmup 3 --no-cpu-baseline --no-extras --scaling weak >> gpurun_out/sweep_c5.jsonl 2>> gpurun_out/sweep_c5.err || echo "{\"failed\": [$n, $q]}" >> gpurun_out/sweep_c5.jsonl
   tail -1 gpurun_out/sweep_c5.jsonl | cut -c1-140
 done
