@@ -144,7 +144,8 @@ static __device__ unsigned long long g_bs_stats[2];
 
 // Plane prefetch: the masks of a column pair are dead once they are parked in the warp's shared-memory slot, so the
 // next pair is loaded into the same registers right after the staging — one pair of prefetch distance (two pairs in
-// flight were measured in round 1 and again in round 2: slower), no second set of registers, no moves.
+// flight were measured in round 1 and again in round 2: slower; so was a prefetch.global.L1 one or two pairs ahead:
+// C2 385 -> 377, C3 673 -> 665 kGCUPS), no second set of registers, no moves.
 #define APC_BS_STAGE_MASKS()                                                                                          \
     s_mask[0][lane] = ma.x; s_mask[0][32 + lane] = ma.y; s_mask[0][64 + lane] = ma.z; s_mask[0][96 + lane] = ma.w;   \
     s_mask[1][lane] = mb.x; s_mask[1][32 + lane] = mb.y; s_mask[1][64 + lane] = mb.z; s_mask[1][96 + lane] = mb.w;
