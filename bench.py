@@ -829,6 +829,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the floor / wide-offset / C2-weak side measurements")
     args = ap.parse_args()
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the host-side set-up (synthetic reads, the oracle) is OpenMP
+    # code: the reference arm (rank 0 alone works) gets every CPU, a B200 rank its share — set before any OpenMP
+    # runtime is loaded
+    if os.environ.get("WORLD_SIZE") and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        share = 1 if args.impl == "reference" else max(1, int(os.environ["WORLD_SIZE"]))
+        os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // share))
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = dict(WORKLOADS[args.workload])
     if args.reads or args.lim:  # C5: the scaling sweep re-sizes a named workload
