@@ -283,7 +283,7 @@ static cudaError_t bs_dispatch(BsLaunchCtx &l) {
     }
 }
 
-// Loads every scan kernel of this k (the twelve unit shapes and the single-k-mer kernel) without launching anything.
+// Loads every scan kernel of this k (the unit shapes and the single-k-mer kernel) without launching anything.
 cudaError_t warm_bs_kernels(const Ctx &c, int k) {
     if (k < 2 || k > 32) return cudaErrorInvalidValue;
     Ctx tmp = c; // only k is looked at

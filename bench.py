@@ -558,6 +558,8 @@ def run_b200(args, w):
         options.append(("plan_alive_pct", args.plan_alive_pct))
     if args.sg_per_job > 0:
         options.append(("tiles_per_job", args.sg_per_job))
+    if args.shape_mask >= 0:
+        options.append(("shape_mask", args.shape_mask))
     if args.graph:
         options.append(("scan_graph", 1))
 
@@ -822,6 +824,8 @@ def main():
                     help="strong (default): one n-read job split over the ranks; weak: every rank holds its own n-read shard")
     ap.add_argument("--plan-alive-pct", type=int, default=-1,
                     help="planner knob (apc_set_option plan_alive_pct): expected share of columns with live deep rows")
+    ap.add_argument("--shape-mask", type=lambda x: int(x, 0), default=-1,
+                    help="tuning knob (apc_set_option shape_mask): bit s = unit shape s may be used")
     ap.add_argument("--sg-per-job", type=int, default=0,
                     help="tuning knob (apc_set_option tiles_per_job): 1024-read super-groups per job, 0 = auto")
     ap.add_argument("--graph", action="store_true", help="replay repeated scans as a CUDA graph (apc_set_option scan_graph 1)")
