@@ -37,7 +37,7 @@ def check_plan(kmers, k):
         if g == 0:
             assert p["units"][s] == 0
             continue
-        assert k - t >= 2 and t >= 1 and k - t + g * t <= 56   # kBsMaxRows
+        assert k - t >= 2 and t >= 1 and k - t + g * t <= 60   # kBsMaxRows
         for _ in range(int(p["units"][s])):
             idx = p["order"][at:at + g]
             rev = p["reversed"][at:at + g]
