@@ -13,6 +13,9 @@ namespace apc {
 constexpr int kGroupsPerSuper = 32; // lanes
 constexpr int kPlaneRow = 128;      // bytes between the A, C, G, T rows of the per-warp mask slot
 
+#ifndef APC_BS_12W_ROWS
+#define APC_BS_12W_ROWS 24
+#endif
 constexpr int bs_warps_per_sm_c(int rows) {
 #ifdef APC_BS_MB_OVERRIDE
     (void)rows;
@@ -20,7 +23,7 @@ constexpr int bs_warps_per_sm_c(int rows) {
 #endif
     // registers are handed out per SM sub-partition (16384 each), so only multiples of 4 warps matter:
     // 24 -> 80 registers, 20 -> 96, 16 -> 128, 12 -> 168, 8 -> 255
-    return rows <= 8 ? 24 : rows <= 12 ? 20 : rows <= 16 ? 16 : rows <= 24 ? 12 : 8;
+    return rows <= 8 ? 24 : rows <= 12 ? 20 : rows <= 16 ? 16 : rows <= APC_BS_12W_ROWS ? 12 : 8;
 }
 
 // Values handed from row i-1 to row i inside one column.
