@@ -411,13 +411,16 @@ int apc_set_queries(apc_ctx *c, uint8_t k, const uint64_t *kmers, uint32_t n_kme
         std::vector<uint32_t> order;
         std::vector<uint8_t> reversed;
         uint32_t shape_mask = variant.pairing() ? c->opt_shape_mask : 0u;
-        // A small sample is bound by parallelism, not by throughput: a job is one unit x 1024 reads walked column by
-        // column, and with fewer jobs than resident warps the scan takes as long as its longest jobs.  Then only the
-        // shapes of at most 31 rows are used (tools/c1_probe.py on C1, 10 000 reads x 500 k-mers: 0.156 -> 0.105 ms
-        // per step; with all shapes excluded 0.164).
+        // A small scan is bound by parallelism, not by throughput: a job is one unit x 1024 reads walked column by
+        // column, and with few jobs per resident warp the scan takes as long as its longest jobs.  So the largest
+        // shapes are left out while there are fewer than 8 jobs per resident warp (units of at most 48 rows: 10 000
+        // reads x 5 000 k-mers 0.54 -> 0.49 ms per step), and below 2 jobs per warp only the shapes of at most 31 rows
+        // are used (tools/c1_probe.py on C1, 10 000 reads x 500 k-mers: 0.156 -> 0.105 ms per step).
         if (c->has_sample && shape_mask == 0xFFFFFFFFu) {
-            const uint64_t n_sg = ((uint64_t)c->n_tiles + 31) / 32;
-            if (n_sg * n_kmers / 6 < 2ull * (uint64_t)c->sm_count * 8) shape_mask = apc::kBsSmallShapes;
+            const uint64_t n_sg = ((uint64_t)c->n_tiles + 31) / 32, jobs = n_sg * n_kmers / 6;
+            const uint64_t warps = (uint64_t)c->sm_count * 8;
+            if (jobs < 2 * warps) shape_mask = apc::kBsSmallShapes;
+            else if (jobs < 8 * warps) shape_mask = apc::kBsMediumShapes;
         }
         apc::bs_group_queries(kmers, n_kmers, k, shape_mask, (float)c->opt_alive_pct / 100.f, order, reversed, units);
         uint64_t *hk = (uint64_t *)c->h_pinned;

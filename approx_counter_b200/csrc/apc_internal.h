@@ -39,6 +39,7 @@ struct BsShape {
 constexpr int kBsShapes = 20;
 constexpr int kBsMaxRows = 60;
 constexpr int kBsAlivePct = 30;
+constexpr uint32_t kBsMediumShapes = 0xFFF00u; // shapes 8..19 of bs_shape: units of at most 48 rows at k = 16
 constexpr uint32_t kBsSmallShapes = 0xFC000u; // shapes 14..19 of bs_shape: units of at most 31 rows at k = 16 (small samples)
 constexpr BsShape bs_shape(int k, int s) {
     // round 2: units of up to 60 rows still compile to 255 registers with at most a few dozen bytes of spills, and
