@@ -240,7 +240,7 @@ def device_count():
     return max(0, n)
 
 
-PLAN_SHAPES = 20  # APC_PLAN_SHAPES (include/apc.h)
+PLAN_SHAPES = 22  # APC_PLAN_SHAPES (include/apc.h)
 
 
 def plan_queries(kmers, k):

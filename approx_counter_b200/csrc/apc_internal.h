@@ -36,18 +36,18 @@ constexpr int kScanWarps = 8;      // warps per CTA of the scan kernel
 struct BsShape {
     int t, g;
 };
-constexpr int kBsShapes = 20;
+constexpr int kBsShapes = 22;
 constexpr int kBsMaxRows = 60;
 constexpr int kBsAlivePct = 30;
-constexpr uint32_t kBsMediumShapes = 0xFFF00u; // shapes 8..19 of bs_shape: units of at most 48 rows at k = 16
-constexpr uint32_t kBsSmallShapes = 0xFC000u; // shapes 14..19 of bs_shape: units of at most 31 rows at k = 16 (small samples)
+constexpr uint32_t kBsMediumShapes = 0x3FFC00u; // shapes 10..21 of bs_shape: units of at most 48 rows at k = 16
+constexpr uint32_t kBsSmallShapes = 0x3F0000u; // shapes 16..21 of bs_shape: units of at most 31 rows at k = 16 (small samples)
 constexpr BsShape bs_shape(int k, int s) {
     // round 2: units of up to 60 rows still compile to 255 registers with at most a few dozen bytes of spills, and
-    // eight larger shapes — greedy selection over the C2 / C3 / C4 query sets with the planner's cost model, each kept
-    // only where the GPU agreed (tools/ab_shapes.sh; (8, 6) was chosen by the model and lost to its spills) — lead
-    // the table: C3 676 -> 829, C4 652 -> 857, C2 385 -> 403 kGCUPS
-    const BsShape table[kBsShapes] = {{4, 10}, {9, 5}, {3, 13}, {6, 7}, {5, 9}, {10, 4}, {7, 5}, {6, 5}, {2, 16}, {6, 6},
-                                      {5, 6},  {8, 4}, {2, 12}, {3, 8}, {6, 3}, {2, 8},  {3, 6}, {3, 4}, {1, 4}, {k - k / 2, 2}};
+    // ten larger shapes — greedy selection over the C2 / C3 / C4 query sets with the planner's cost model, each kept
+    // only where the GPU agreed (tools/ab_shapes.sh; (8, 6) and (7, 7) were chosen by the model and lost to their
+    // spills) — lead the table: C3 676 -> 838, C4 652 -> 857, C2 385 -> 408 kGCUPS
+    const BsShape table[kBsShapes] = {{4, 10}, {9, 5}, {3, 13}, {6, 7}, {5, 9}, {3, 14}, {10, 4}, {7, 5}, {8, 5}, {6, 5}, {2, 16},
+                                      {6, 6},  {5, 6}, {8, 4},  {2, 12}, {3, 8}, {6, 3}, {2, 8},  {3, 6},  {3, 4}, {1, 4}, {k - k / 2, 2}};
     const BsShape sh = table[s];
     const int p = k - sh.t;
     if (p < 2 || sh.t < 1 || p + sh.g * sh.t > kBsMaxRows) return BsShape{0, 0};

@@ -231,7 +231,7 @@ int apc_set_option(apc_ctx *ctx, const char *name, int64_t value);
  * and members per unit of each shape for this k (0 where the shape does not
  * exist).  Any output pointer may be NULL.  Introspection for tests and
  * tuning; the counts do not depend on the plan. */
-#define APC_PLAN_SHAPES 20
+#define APC_PLAN_SHAPES 22
 int apc_plan_queries(uint8_t k, const uint64_t *kmers, uint32_t n_kmers,
                      uint32_t *order_out, uint8_t *reversed_out,
                      uint32_t *units_out, int32_t *shape_t_out,

@@ -12,7 +12,7 @@ dev = torch.device("cuda", 0)
 ends = [host.synth_ends(w["seed"], 0, n, sl, b) for b in (False, True)]
 thr = host.adjust_threshold(1.0, 16, k)
 streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
-for mask, graph, two in [(0xFFFFF, 0, 0), (0xFFFFF, 1, 0), (0xFFFFF, 0, 1), (0xFFFFF, 1, 1), (0xFC000, 0, 0), (0xFC000, 0, 1), (0xE0000, 0, 1), (0, 0, 0), (0, 0, 1)]:
+for mask, graph, two in [(0x3FFFFF, 0, 0), (0x3FFFFF, 1, 0), (0x3FFFFF, 0, 1), (0x3FFFFF, 1, 1), (0x3F0000, 0, 0), (0x3F0000, 0, 1), (0x380000, 0, 1), (0, 0, 0), (0, 0, 1)]:
     ctxs = [ApproxCounter(0), ApproxCounter(0)]
     outs = []
     for c, s, st in zip(ctxs, ends, streams):
