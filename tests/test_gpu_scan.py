@@ -443,3 +443,51 @@ def test_reserve_changes_nothing_but_the_first_call_cost(built):
         assert np.array_equal(res[1][4], orc.error_count(codes, offs, res[1][0], 16, fast=True))
         st = warm.scan_stats()
         assert st["scans"] == 1                           # the dummy run is not in the tally
+
+
+@pytest.mark.parametrize("k", [16, 19, 20, 27, 32])
+def test_every_unit_shape_alone(built, k):
+    """Each unit shape on its own (shape_mask = one bit): a family of exactly G k-mers sharing K - T bases, forwards and
+    — reversed — backwards, on a sample in which the family's trunk and its variants are planted with errors.  This is
+    the direct check of every group-kernel instantiation of these k, the 60-row units included."""
+    from approx_counter_b200 import ApproxCounter, plan_queries
+    rng = np.random.default_rng(4200 + k)
+    shapes = plan_queries(np.array([0], np.uint64), k)
+    trunk = rng.choice(ACGT, size=k)
+    n, L = 4096, 64 + k
+    sample = rng.choice(ACGT, size=(n, L))
+    for r in range(n):
+        if r % 2 == 0:
+            m = bytearray(trunk.tobytes())
+            for _ in range(int(rng.integers(0, 3))):        # a tail variant: edits in the second half
+                m[int(rng.integers(k // 2, k))] = int(rng.choice(ACGT))
+            m = mutate(rng, bytes(m), int(rng.integers(0, 3)))[:L]
+            if r % 4 == 0:
+                m = m[::-1]                                  # what the backward-walking units look for
+            pos = int(rng.choice([0, L - len(m), int(rng.integers(0, L - len(m) + 1))]))
+            sample[r, pos:pos + len(m)] = np.frombuffer(m, np.uint8)
+    sample[rng.random((n, L)) < 0.002] = ord("N")
+    codes, offs = orc.encode_matrix(sample)
+    with ApproxCounter(0) as c:
+        c.upload_sample(sample)
+        tested = 0
+        for s in range(len(shapes["shape_g"])):
+            t, g = int(shapes["shape_t"][s]), int(shapes["shape_g"][s])
+            if g == 0:
+                continue
+            fam = set()
+            while len(fam) < g:                              # G members: the trunk's first K - T bases + distinct tails
+                tail = rng.choice(ACGT, size=t)
+                fam.add(trunk[: k - t].tobytes() + tail.tobytes())
+            fw = [orc.dna2int(x.decode()) for x in sorted(fam)]
+            bw = [orc.dna2int(x[::-1].decode()) for x in sorted(fam)]      # share a SUFFIX: scanned reversed
+            kmers = np.array(fw + bw + [int(x) for x in rng.integers(0, 1 << 30, 3)], np.uint64)
+            want = orc.error_count(codes, offs, kmers, k, fast=True)
+            c.set_option("shape_mask", 1 << s)
+            got = c.errorCount(kmers, k)
+            assert np.array_equal(got, want), (k, s, t, g)
+            st = c.scan_stats()
+            # the family really ran as units of this shape: fewer planned rows than one k-mer per warp
+            assert st["lop3_planned"] < st["lop3_one_kmer_per_warp"], (k, s, t, g)
+            tested += 1
+        assert tested >= 12
