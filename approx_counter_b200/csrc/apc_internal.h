@@ -63,7 +63,9 @@ constexpr int bs_check_row_host(int k) {
 #else
     // A/B on the BASELINE workloads (tools/ab_skip.sh): k = 16: row 12 / 13 / 14 -> 346 / 365 / 353 kGCUPS;
     // k = 20: 549 / 618 / 625; k = 32: 13 / 14 -> 556 / 585
-    return k >= 18 ? 14 : k >= 16 ? 13 : k;
+    // round 2, with the larger units (tools/ab_bench.sh): k = 16: 12 / 13 / 14 -> 371 / 403 / 382; k = 20: 13 / 14 / 15 ->
+    // 788 / 831 / 795; k = 32: 13 / 14 / 15 -> 784 / 859 / 866
+    return k >= 28 ? 15 : k >= 18 ? 14 : k >= 16 ? 13 : k;
 #endif
 }
 // The scan kernels prefetch one column pair past either end of a read: the plane buffer is padded by that much.
