@@ -15,6 +15,7 @@ APC_OK = 0
 ERRORS = {
     -1: "APC_ERR_INVALID", -2: "APC_ERR_CUDA", -3: "APC_ERR_NO_DEVICE", -4: "APC_ERR_NO_SAMPLE",
     -5: "APC_ERR_NO_QUERIES", -6: "APC_ERR_NOMEM", -7: "APC_ERR_CAPACITY", -8: "APC_ERR_COMM",
+    -9: "APC_ERR_FORMAT",
 }
 
 # every symbol include/apc.h declares: (restype, argtypes)
@@ -47,6 +48,11 @@ SYMBOLS = {
     "apc_upload_sample_async": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint32]),
     "apc_upload_sample_ragged": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
     "apc_sample_info": (C.c_int, [_vp, _u64p, C.POINTER(C.c_uint32), _u64p]),
+    "apc_ingest_fastx": (C.c_int, [_vp, _vp, C.c_uint64, _u64p, C.POINTER(C.c_int)]),
+    "apc_ingest_lengths": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
+    "apc_sample_resident": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, _u64p]),
+    "apc_download_sample": (C.c_int, [_vp, _vp, C.c_uint64]),
+    "apc_ingest_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "apc_exact_topn": (C.c_int, [_vp, C.c_uint8, C.c_float, C.c_uint64, _vp, C.c_uint64,
                                  _vp, _vp, _u64p, _u64p, _u64p]),
     "apc_exact_solid": (C.c_int, [_vp, C.c_uint8, C.c_float, C.c_uint64, _vp, C.c_uint64,

@@ -105,6 +105,51 @@ class ApproxCounter:
         self._check(self._lib.apc_sample_info(self._h, C.byref(n), C.byref(ml), C.byref(tb)))
         return n.value, ml.value, tb.value
 
+    # -- ingest on the device (:819-825 + :415-476) ---------------------------------
+    def ingest_fastx(self, data):
+        """data: the bytes of a FASTA / FASTQ file (bytes, bytearray, mmap or uint8 array).  Copies them to
+        HBM and indexes the records there (apc_ingest_fastx) -> (n_records, is_fastq).  Raises ApcError
+        with status APC_ERR_FORMAT (-9) for wrapped records and other input the device parser leaves to
+        the host parser (host.Reads)."""
+        a = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+        n, fq = C.c_uint64(), C.c_int()
+        st = self._lib.apc_ingest_fastx(self._h, a.ctypes.data if a.size else None, a.size, C.byref(n), C.byref(fq))
+        if st != _lib.APC_OK:
+            raise ApcError(st, self._lib.apc_last_error(self._h).decode())
+        self._n_records = n.value
+        return n.value, bool(fq.value)
+
+    def ingest_lengths(self, first=0, n=None):
+        n = self._n_records - first if n is None else n
+        out = np.zeros(n, np.uint32)
+        self._check(self._lib.apc_ingest_lengths(self._h, int(first), int(n), out.ctypes.data))
+        return out
+
+    def sample_resident(self, nb_sample, cut, bot, order=None):
+        """sampleSequences (:415-476) on the device over the ingested file; `order`: the shuffled read ids
+        (host.shuffle_order), None = file order.  The context then holds the sample.  -> n_sampled."""
+        n = C.c_uint64()
+        if order is None:
+            st = self._lib.apc_sample_resident(self._h, None, 0, int(nb_sample), int(cut), int(bool(bot)), C.byref(n))
+        else:
+            o = np.ascontiguousarray(order, np.uint32)
+            st = self._lib.apc_sample_resident(self._h, o.ctypes.data, len(o), int(nb_sample), int(cut), int(bool(bot)),
+                                               C.byref(n))
+        self._check(st)
+        return n.value
+
+    def download_sample(self):
+        """ASCII rows of the resident sample -> uint8[n_reads, read_len]."""
+        n, ml, _ = self.sample_info()
+        out = np.zeros((n, ml), np.uint8)
+        self._check(self._lib.apc_download_sample(self._h, out.ctypes.data if out.size else None, out.size))
+        return out
+
+    def ingest_timing(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        self._check(self._lib.apc_ingest_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"copy_ms": a.value, "index_ms": b.value, "sample_ms": c.value}
+
     # -- exact stage (:487-519 + :396-405) ------------------------------------------
     def count_kmers_topn(self, k, lc_adjusted, lim, forbidden=None):
         """-> (kmers u64[n], counts u64[n], n_distinct, had_n), CompareCount order."""

@@ -104,6 +104,7 @@ const char *apc_strerror(int status) {
     case APC_ERR_NOMEM: return "out of memory";
     case APC_ERR_CAPACITY: return "output capacity too small";
     case APC_ERR_COMM: return "communicator (NCCL) error";
+    case APC_ERR_FORMAT: return "input outside the device parser's grammar (use the host parser)";
     default: return "unknown status";
     }
 }
@@ -136,6 +137,8 @@ int apc_create(int device, apc_ctx **out) {
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_deep_lop3, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(c->d_deep_lop3, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->bs_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&c->ev_ingest[i]);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_ingest_flag, 4 * sizeof(uint32_t));
     for (int i = 0; i < apc::kBsShapes && e == cudaSuccess; i++) {
         e = cudaStreamCreateWithFlags(&c->bs_streams[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->bs_join[i], cudaEventDisableTiming);
@@ -168,6 +171,16 @@ void apc_destroy(apc_ctx *c) {
     cudaFree(c->d_stage);
     cudaFree(c->d_stage_offs);
     apc::free_exact_scratch(c);
+    cudaFree(c->d_file);
+    cudaFree(c->d_tile_nl);
+    cudaFree(c->d_nl);
+    cudaFree(c->d_rec_start);
+    cudaFree(c->d_rec_len);
+    cudaFree(c->d_pick);
+    cudaFree(c->d_ingest_temp);
+    cudaFree(c->d_ingest_flag);
+    for (auto &e : c->ev_ingest)
+        if (e) cudaEventDestroy(e);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto &e : c->ev)
         if (e) cudaEventDestroy(e);
@@ -204,6 +217,7 @@ int apc_upload_sample_async(apc_ctx *c, const uint8_t *bases, uint64_t n_reads, 
     const size_t bytes = (size_t)n_reads * read_len;
     if ((st = apc::prepare_sample(c, n_reads, read_len, bytes))) return st;
     c->uniform_len = true;
+    c->stage_is_sample = false;
     if ((st = apc::grow(c, c->d_stage, c->stage_cap, bytes))) return st;
     if (bytes) APC_CUDA(c, cudaMemcpyAsync(c->d_stage, bases, bytes, cudaMemcpyHostToDevice, c->stream));
     APC_CUDA(c, apc::launch_build_tiles_uniform(c->d_stage, n_reads, read_len, c->chunks, c->n_tiles,
@@ -211,6 +225,7 @@ int apc_upload_sample_async(apc_ctx *c, const uint8_t *bases, uint64_t n_reads, 
     APC_CUDA(c, apc::launch_build_planes(*c));
     APC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     c->has_sample = true;
+    c->stage_is_sample = true;
     c->timing.upload_ms = -1.f; // resolved lazily by apc_last_timing
     return APC_OK;
 }
@@ -248,6 +263,7 @@ int apc_upload_sample_ragged(apc_ctx *c, const uint8_t *bases, const uint64_t *o
     APC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     if ((st = apc::prepare_sample(c, n_reads, max_len, total))) return st;
     c->uniform_len = false;
+    c->stage_is_sample = false;
     if ((st = apc::grow(c, c->d_stage, c->stage_cap, (size_t)total))) return st;
     if ((st = apc::grow(c, c->d_stage_offs, c->stage_offs_cap, (size_t)(n_reads + 1) * sizeof(uint64_t)))) return st;
     if (n_reads) {
@@ -268,6 +284,166 @@ int apc_upload_sample_ragged(apc_ctx *c, const uint8_t *bases, const uint64_t *o
     c->timing.upload_ms = apc::elapsed(c->ev[0], c->ev[1]);
     return APC_OK;
     APC_CATCH(c)
+}
+
+// ---- ingest on the device (ingest_kernels.cu) ---------------------------------------------------------------
+int apc_ingest_fastx(apc_ctx *c, const uint8_t *file_bytes, uint64_t n_bytes, uint64_t *n_records_out, int *is_fastq_out) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (!file_bytes && n_bytes) return apc::fail(c, APC_ERR_INVALID, "file_bytes is NULL");
+    c->has_file = false;
+    c->n_records = 0;
+    if (n_records_out) *n_records_out = 0;
+    if (is_fastq_out) *is_fastq_out = 0;
+    // blank lines at the end of the file are dropped here: the last line of what is copied is never empty
+    uint64_t n_eff = n_bytes;
+    while (n_eff > 0) {
+        const uint8_t ch = file_bytes[n_eff - 1];
+        if (ch != '\n' && ch != '\r' && ch != ' ' && ch != '\t') break;
+        n_eff--;
+    }
+    c->file_bytes = n_eff;
+    c->ingest_ms[0] = c->ingest_ms[1] = 0.f;
+    if (n_eff == 0) { // no record at all
+        c->has_file = true;
+        c->file_fastq = 0;
+        return APC_OK;
+    }
+    if (file_bytes[0] != '>' && file_bytes[0] != '@')
+        return apc::fail(c, APC_ERR_FORMAT, "input does not start with '>' or '@'");
+    const bool fastq = file_bytes[0] == '@';
+    const uint64_t n_tiles = (n_eff + apc::kIngestTileBytes - 1) / apc::kIngestTileBytes;
+    const uint64_t padded = n_tiles * apc::kIngestTileBytes;
+    if ((st = apc::grow(c, c->d_file, c->file_cap, (size_t)padded))) return st;
+    if ((st = apc::grow(c, c->d_tile_nl, c->tile_nl_cap, (size_t)(n_tiles + 1) * sizeof(uint64_t)))) return st;
+    size_t temp_bytes = 0;
+    APC_CUDA(c, apc::ingest_prefix_u64(nullptr, temp_bytes, c->d_tile_nl, n_tiles + 1, c->stream));
+    if ((st = apc::grow(c, c->d_ingest_temp, c->ingest_temp_cap, temp_bytes))) return st;
+    APC_CUDA(c, cudaEventRecord(c->ev_ingest[0], c->stream));
+    // pageable memory is staged by the driver; pieces keep its staging buffers busy without a giant single request
+    for (uint64_t off = 0; off < n_eff; off += (uint64_t)64 << 20) {
+        const uint64_t len = std::min<uint64_t>((uint64_t)64 << 20, n_eff - off);
+        APC_CUDA(c, cudaMemcpyAsync(c->d_file + off, file_bytes + off, len, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (padded > n_eff) APC_CUDA(c, cudaMemsetAsync(c->d_file + n_eff, 0, padded - n_eff, c->stream));
+    APC_CUDA(c, cudaEventRecord(c->ev_ingest[1], c->stream));
+    APC_CUDA(c, cudaMemsetAsync(c->d_tile_nl + n_tiles, 0, sizeof(uint64_t), c->stream));
+    APC_CUDA(c, cudaMemsetAsync(c->d_ingest_flag, 0, 4 * sizeof(uint32_t), c->stream));
+    APC_CUDA(c, apc::launch_count_newlines(c->d_file, n_tiles, c->d_tile_nl, c->stream));
+    temp_bytes = c->ingest_temp_cap;
+    APC_CUDA(c, apc::ingest_prefix_u64(c->d_ingest_temp, temp_bytes, c->d_tile_nl, n_tiles + 1, c->stream));
+    uint64_t n_nl = 0;
+    APC_CUDA(c, cudaMemcpyAsync(&n_nl, c->d_tile_nl + n_tiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    const uint64_t n_lines = n_nl + 1, per = fastq ? 4 : 2;
+    if (n_lines % per)
+        return apc::fail(c, APC_ERR_FORMAT, fastq ? "line count is not a multiple of 4 (not 4-line FASTQ)"
+                                                 : "line count is odd (not single-line FASTA)");
+    const uint64_t n_rec = n_lines / per;
+    if (n_rec > 0x7FFFFFFFull) return apc::fail(c, APC_ERR_INVALID, "too many records (the reference's read ids are int)");
+    if ((st = apc::grow(c, c->d_nl, c->nl_cap, (size_t)std::max<uint64_t>(1, n_nl) * sizeof(uint64_t)))) return st;
+    if ((st = apc::grow(c, c->d_rec_start, c->rec_start_cap, (size_t)n_rec * sizeof(uint64_t)))) return st;
+    if ((st = apc::grow(c, c->d_rec_len, c->rec_len_cap, (size_t)n_rec * sizeof(uint32_t)))) return st;
+    APC_CUDA(c, apc::launch_write_newlines(c->d_file, n_tiles, c->d_tile_nl, c->d_nl, c->stream));
+    APC_CUDA(c, apc::launch_index_records(c->d_file, c->d_nl, n_nl, n_eff, fastq, n_rec, c->d_rec_start, c->d_rec_len,
+                                          c->d_ingest_flag, c->stream));
+    APC_CUDA(c, cudaEventRecord(c->ev_ingest[2], c->stream));
+    uint32_t flag = 0;
+    APC_CUDA(c, cudaMemcpyAsync(&flag, c->d_ingest_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->ingest_ms[0] = apc::elapsed(c->ev_ingest[0], c->ev_ingest[1]);
+    c->ingest_ms[1] = apc::elapsed(c->ev_ingest[1], c->ev_ingest[2]);
+    if (flag)
+        return apc::fail(c, APC_ERR_FORMAT, fastq ? "not 4-line FASTQ (wrapped record, blank line, or quality length)"
+                                                 : "not single-line FASTA (wrapped record, blank line, or blanks in a sequence)");
+    c->has_file = true;
+    c->file_fastq = fastq ? 1 : 0;
+    c->n_records = n_rec;
+    if (n_records_out) *n_records_out = n_rec;
+    if (is_fastq_out) *is_fastq_out = c->file_fastq;
+    return APC_OK;
+}
+
+int apc_ingest_lengths(apc_ctx *c, uint64_t first, uint64_t n, uint32_t *lens_out) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (!c->has_file) return apc::fail(c, APC_ERR_NO_SAMPLE, "apc_ingest_fastx first");
+    if (first > c->n_records || n > c->n_records - first || (!lens_out && n)) return apc::fail(c, APC_ERR_INVALID, "range");
+    if (n) APC_CUDA(c, cudaMemcpyAsync(lens_out, c->d_rec_len + first, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return APC_OK;
+}
+
+int apc_sample_resident(apc_ctx *c, const uint32_t *order, uint64_t n_order, uint64_t nb_sample, uint32_t cut, int bot,
+                        uint64_t *n_sampled_out) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (n_sampled_out) *n_sampled_out = 0;
+    if (!c->has_file) return apc::fail(c, APC_ERR_NO_SAMPLE, "apc_ingest_fastx first");
+    const uint64_t n = c->n_records;
+    if (order && n_order != n) return apc::fail(c, APC_ERR_INVALID, "order must hold every record id once");
+    if (cut > 0x7FFFFFF0u) return apc::fail(c, APC_ERR_INVALID, "cut too large");
+    const uint32_t row_len = cut + (bot ? 1u : 0u);
+    APC_CUDA(c, cudaEventRecord(c->ev_ingest[2], c->stream));
+    uint64_t n_sampled = 0;
+    uint32_t *d_ord = nullptr, *d_flags = nullptr, *d_pos = nullptr, *d_chosen = nullptr;
+    if (n && cut && nb_sample) { // :461 takes nothing when cut == 0 (current_cut_size > 0 is part of the test)
+        if ((st = apc::grow(c, c->d_pick, c->pick_cap, (size_t)n * 4 * sizeof(uint32_t)))) return st;
+        d_ord = c->d_pick, d_flags = d_ord + n, d_pos = d_flags + n, d_chosen = d_pos + n;
+        size_t temp_bytes = 0;
+        APC_CUDA(c, apc::ingest_prefix_u32(nullptr, temp_bytes, d_flags, d_pos, n, c->stream));
+        if ((st = apc::grow(c, c->d_ingest_temp, c->ingest_temp_cap, temp_bytes))) return st;
+        if (order) APC_CUDA(c, cudaMemcpyAsync(d_ord, order, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        APC_CUDA(c, cudaMemsetAsync(c->d_ingest_flag, 0, 4 * sizeof(uint32_t), c->stream));
+        APC_CUDA(c, apc::launch_pick_reads(order ? d_ord : nullptr, n, c->d_rec_len, 2ull * cut, nb_sample, d_flags, d_pos,
+                                           d_chosen, c->d_ingest_temp, c->ingest_temp_cap, c->d_ingest_flag, c->stream));
+        uint32_t last[2] = {0, 0}, flag = 0;
+        APC_CUDA(c, cudaMemcpyAsync(&last[0], d_pos + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        APC_CUDA(c, cudaMemcpyAsync(&last[1], d_flags + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        APC_CUDA(c, cudaMemcpyAsync(&flag, c->d_ingest_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        APC_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (flag) return apc::fail(c, APC_ERR_INVALID, "order holds an id outside [0, n_records)");
+        n_sampled = std::min<uint64_t>(nb_sample, (uint64_t)last[0] + last[1]);
+    }
+    const size_t bytes = (size_t)n_sampled * row_len;
+    if ((st = apc::prepare_sample(c, n_sampled, row_len, bytes))) return st;
+    c->uniform_len = true;
+    c->stage_is_sample = false;
+    if ((st = apc::grow(c, c->d_stage, c->stage_cap, bytes))) return st;
+    APC_CUDA(c, apc::launch_gather_ends(c->d_file, c->d_rec_start, c->d_rec_len, d_chosen, n_sampled, row_len, cut, bot != 0,
+                                        c->d_stage, c->stream));
+    APC_CUDA(c, apc::launch_build_tiles_uniform(c->d_stage, n_sampled, row_len, c->chunks, c->n_tiles, c->d_tiles, c->d_lens,
+                                                c->stream));
+    APC_CUDA(c, apc::launch_build_planes(*c));
+    APC_CUDA(c, cudaEventRecord(c->ev_ingest[3], c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->has_sample = true;
+    c->stage_is_sample = true;
+    c->ingest_ms[2] = apc::elapsed(c->ev_ingest[2], c->ev_ingest[3]);
+    c->timing.upload_ms = c->ingest_ms[2];
+    if (n_sampled_out) *n_sampled_out = n_sampled;
+    return APC_OK;
+}
+
+int apc_download_sample(apc_ctx *c, uint8_t *bases_out, uint64_t capacity) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (!c->has_sample) return apc::fail(c, APC_ERR_NO_SAMPLE, "no sample");
+    if (!c->uniform_len || !c->stage_is_sample) return apc::fail(c, APC_ERR_INVALID, "the resident sample has no ASCII rows");
+    const uint64_t bytes = c->n_reads * c->max_len;
+    if (bytes > capacity) return apc::fail(c, APC_ERR_CAPACITY, "capacity");
+    if (bytes && !bases_out) return apc::fail(c, APC_ERR_INVALID, "bases_out is NULL");
+    if (bytes) APC_CUDA(c, cudaMemcpyAsync(bases_out, c->d_stage, bytes, cudaMemcpyDeviceToHost, c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    return APC_OK;
+}
+
+int apc_ingest_timing(const apc_ctx *c, float *copy_ms, float *index_ms, float *sample_ms) {
+    if (!c) return APC_ERR_INVALID;
+    if (copy_ms) *copy_ms = c->ingest_ms[0];
+    if (index_ms) *index_ms = c->ingest_ms[1];
+    if (sample_ms) *sample_ms = c->ingest_ms[2];
+    return APC_OK;
 }
 
 int apc_reserve(apc_ctx *c, uint64_t n_reads, uint32_t read_len, uint8_t k, uint32_t n_kmers) {

@@ -177,6 +177,30 @@ struct Ctx {
     void *h_pinned = nullptr;
     size_t pinned_cap = 0;
 
+    // resident input file and its record index (device ingest, ingest_kernels.cu)
+    uint8_t *d_file = nullptr;       // the file's bytes, padded with zeros to a whole number of 16 KB tiles
+    size_t file_cap = 0;
+    uint64_t *d_tile_nl = nullptr;   // newlines per tile, then (in place) their exclusive prefix sum; [tiles + 1]
+    size_t tile_nl_cap = 0;
+    uint64_t *d_nl = nullptr;        // byte offsets of the newlines, ascending
+    size_t nl_cap = 0;
+    uint64_t *d_rec_start = nullptr; // per record: byte offset of its sequence line
+    size_t rec_start_cap = 0;
+    uint32_t *d_rec_len = nullptr;   // per record: bases on that line
+    size_t rec_len_cap = 0;
+    uint32_t *d_pick = nullptr;      // sampling scratch: order | eligible flags | their prefix sum | chosen ids, n u32 each
+    size_t pick_cap = 0;
+    void *d_ingest_temp = nullptr;   // cub temp storage of the two prefix sums
+    size_t ingest_temp_cap = 0;
+    uint32_t *d_ingest_flag = nullptr; // [0] malformed input seen by a kernel
+    cudaEvent_t ev_ingest[4] = {};   // copy 0-1, index 1-2, sample 2-3 (of the most recent calls)
+    bool has_file = false;
+    bool stage_is_sample = false;    // d_stage holds the ASCII rows of the resident sample (apc_download_sample)
+    int file_fastq = 0;
+    uint64_t file_bytes = 0;         // without trailing blank lines
+    uint64_t n_records = 0;
+    float ingest_ms[3] = {0.f, 0.f, 0.f}; // copy, index, sample
+
     // options
     int opt_variant = 0;
     int opt_tiles_per_job = 0;
@@ -210,6 +234,24 @@ cudaError_t launch_build_tiles_uniform(const uint8_t *d_ascii, uint64_t n_reads,
 cudaError_t launch_build_tiles_ragged(const uint8_t *d_ascii, const uint64_t *d_offs, uint64_t n_reads,
                                       uint32_t chunks, uint32_t n_tiles, uint4 *d_tiles,
                                       uint32_t *d_lens, cudaStream_t s);
+
+// ingest_kernels.cu
+constexpr uint64_t kIngestTileBytes = 16384;
+cudaError_t launch_count_newlines(const uint8_t *d_file, uint64_t n_tiles, uint64_t *d_tile_nl, cudaStream_t s);
+cudaError_t launch_write_newlines(const uint8_t *d_file, uint64_t n_tiles, const uint64_t *d_tile_base, uint64_t *d_nl,
+                                  cudaStream_t s);
+cudaError_t ingest_prefix_u64(void *d_temp, size_t &temp_bytes, uint64_t *d_inout, uint64_t n, cudaStream_t s);
+cudaError_t ingest_prefix_u32(void *d_temp, size_t &temp_bytes, const uint32_t *d_in, uint32_t *d_out, uint64_t n,
+                              cudaStream_t s);
+cudaError_t launch_index_records(const uint8_t *d_file, const uint64_t *d_nl, uint64_t n_nl, uint64_t n_bytes, bool fastq,
+                                 uint64_t n_records, uint64_t *d_rec_start, uint32_t *d_rec_len, uint32_t *d_flag,
+                                 cudaStream_t s);
+cudaError_t launch_pick_reads(const uint32_t *d_order, uint64_t n, const uint32_t *d_rec_len, uint64_t min_len,
+                              uint64_t nb_sample, uint32_t *d_flags, uint32_t *d_pos, uint32_t *d_chosen, void *d_temp,
+                              size_t temp_bytes, uint32_t *d_flag, cudaStream_t s);
+cudaError_t launch_gather_ends(const uint8_t *d_file, const uint64_t *d_rec_start, const uint32_t *d_rec_len,
+                               const uint32_t *d_chosen, uint64_t n_sampled, uint32_t row_len, uint32_t cut, bool bot,
+                               uint8_t *d_stage, cudaStream_t s);
 
 // scan_kernel.cu
 ScanVariant pick_variant(int k, int forced);

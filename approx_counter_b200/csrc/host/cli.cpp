@@ -4,7 +4,13 @@
 // with the two hot functions replaced by libapc's C ABI:
 //   count_kmers + get_most_frequent (:874, :898) -> apc_exact_topn
 //   errorCount                      (:922)       -> apc_approx_count
-// Extensions (not in the reference): --seed, --gpus, --device.
+//   readRecords + sampleSequences   (:825, :867) -> apc_ingest_fastx + apc_sample_resident with --ingest device
+// Extensions (not in the reference): --seed, --gpus, --device, --ingest.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <array>
 #include <chrono>
 #include <cstdio>
@@ -35,6 +41,35 @@ void print(const T &text, int tab = 0) { // :85-94
     std::cout << text << std::endl;
 }
 
+// read-only mapping of the input, paged in by the kernel while mmap runs (MAP_POPULATE) — --ingest device
+struct MappedFile {
+    const uint8_t *data = nullptr;
+    size_t size = 0;
+    bool open(const std::string &path) {
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+            ::close(fd);
+            return false;
+        }
+        size = (size_t)st.st_size;
+        if (size) {
+            void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+            if (m == MAP_FAILED) {
+                ::close(fd);
+                return false;
+            }
+            data = (const uint8_t *)m;
+        }
+        ::close(fd);
+        return true;
+    }
+    ~MappedFile() {
+        if (data) munmap((void *)data, size);
+    }
+};
+
 enum class Kind { Int, Double, String, Flag };
 struct OptSpec {
     const char *short_name, *long_name;
@@ -62,6 +97,9 @@ const OptSpec OPTIONS[] = {
     {"", "seed", Kind::Int, "[extension] seed of the read shuffle (default: std::random_device, like the reference)"},
     {"", "gpus", Kind::Int, "[extension] number of GPUs to shard the sampled reads over (default 1)"},
     {"", "device", Kind::Int, "[extension] first CUDA device to use (default 0)"},
+    {"", "ingest", Kind::String,
+     "[extension] host (default): the input is parsed and sampled by host threads; device: its bytes are copied to the "
+     "GPU, indexed and sampled there (single-line FASTA / 4-line FASTQ, one GPU; anything else falls back to host)"},
     {"", "version-check", Kind::String, "[accepted for SeqAn compatibility, ignored]"},
 };
 
@@ -178,6 +216,7 @@ int cli_main(int argc, const char **argv) {
     float lc = 1.0;
     uint64_t n_gpus = 1, device0 = 0;
     int64_t seed = -1;
+    std::string ingest = "host";
 
     get_str(parser, "config", config_file);
     if (!config_file.empty()) { // :721-737
@@ -215,6 +254,7 @@ int cli_main(int argc, const char **argv) {
     get_u64(parser, "multi_run", nb_of_runs);
     get_u64(parser, "gpus", n_gpus);
     get_u64(parser, "device", device0);
+    get_str(parser, "ingest", ingest);
     if (parser.isSet("seed")) seed = std::strtoll(parser.values["seed"].c_str(), nullptr, 10);
     skip_end = skip_end || parser.isSet("skip_end"); // :758
 
@@ -278,13 +318,47 @@ int cli_main(int argc, const char **argv) {
         ~Joiner() { if (t.joinable()) t.join(); }
     } creator_guard{creator};
 
+    if (ingest != "host" && ingest != "device") {
+        std::cerr << error_pref << "--ingest takes host or device" << std::endl;
+        return 1;
+    }
     if (v > 0) print("Parsing FASTA file", tab_level); // :821-825
     Reads seqs;
-    {
+    uint64_t n_seqs = 0;
+    bool device_ingest = false;
+    if (ingest == "device" && n_gpus == 1) {
+        // The file is mapped and paged in beside the creation of the CUDA context, then copied to the GPU, where the
+        // records are indexed and every sample is gathered (apc_ingest_fastx / apc_sample_resident).
+        MappedFile file;
+        if (!file.open(input_file)) {
+            std::cerr << error_pref << "could not open " << input_file << std::endl;
+            return 1;
+        }
+        if (v > 1) print("File mapped; waiting for the CUDA context", tab_level);
+        creator.join();
+        if (create_status != APC_OK) return gpu_fail("cannot open CUDA device", nullptr, create_status);
+        int is_fastq = 0;
+        const int st = apc_ingest_fastx(gpus[0].ctx, file.data, file.size, &n_seqs, &is_fastq);
+        if (st == APC_OK) {
+            device_ingest = true;
+            if (v > 1) {
+                float copy_ms = 0.f, index_ms = 0.f;
+                apc_ingest_timing(gpus[0].ctx, &copy_ms, &index_ms, nullptr);
+                print(std::string(is_fastq ? "FASTQ" : "FASTA") + " indexed on the GPU (copy " + std::to_string(copy_ms) +
+                          " ms, index " + std::to_string(index_ms) + " ms)", tab_level);
+            }
+        } else if (st == APC_ERR_FORMAT) {
+            if (v > 1) print(std::string("Device parser: ") + apc_last_error(gpus[0].ctx) + "; using the host parser", tab_level);
+        } else {
+            return gpu_fail("copying the input to the GPU", gpus[0].ctx, st);
+        }
+    }
+    if (!device_ingest) {
         std::string err;
         const bool parsed = read_fastx(input_file, seqs, err);
+        n_seqs = seqs.size();
         if (v > 1) print("File parsed; waiting for the CUDA context", tab_level);
-        creator.join();
+        if (creator.joinable()) creator.join();
         if (v > 1)
             print("CUDA context ready (beside the parsing: context " + std::to_string(create_ms) + " ms, buffers and kernels " +
                       std::to_string(reserve_ms) + " ms)", tab_level);
@@ -318,13 +392,13 @@ int cli_main(int argc, const char **argv) {
             print("NCCL communicator over " + std::to_string(n_gpus) + " GPUs", tab_level);
         }
     }
-    if (v > 0) print("Number of sequences found: " + std::to_string(seqs.size()) + ".", tab_level);
+    if (v > 0) print("Number of sequences found: " + std::to_string(n_seqs) + ".", tab_level);
 
     std::string run_suffix;
     for (uint64_t current_run = 0; current_run < nb_of_runs; current_run++) { // :835
         run_suffix = "_" + std::to_string(current_run);                       // :837 (always appended)
         if (nb_of_runs > 1 && v > 0) std::cout << "Starting run number " << current_run + 1 << std::endl;
-        const uint64_t sequence_set_size = seqs.size();
+        const uint64_t sequence_set_size = n_seqs;
         if (sn > sequence_set_size) { // :844-848
             std::cerr << warning << "Sequence set too small for the requested sample size\n";
             std::cerr << warning << "The whole set will be used.\n";
@@ -340,10 +414,20 @@ int cli_main(int argc, const char **argv) {
             if (mr_v > 0) print(bottom ? "Sampling the ends of reads" : "Sampling the start of reads", 1);
             uint64_t n_sampled = 0;
             uint32_t row_len = 0;
-            const std::vector<uint8_t> sample = sample_sequences(seqs, sn, sl, bottom, seed, n_sampled, row_len); // :867
+            std::vector<uint8_t> sample;
+            int st = APC_OK;
+            if (device_ingest) { // :867 on the device: the host only shuffles the ids (:423-429)
+                const std::vector<int> order = shuffle_order(n_seqs, seed);
+                st = apc_sample_resident(ctx0, reinterpret_cast<const uint32_t *>(order.data()), order.size(), sn,
+                                         (uint32_t)sl, bottom ? 1 : 0, &n_sampled);
+                if (st != APC_OK) return gpu_fail("sampling on the GPU", ctx0, st);
+                row_len = (uint32_t)(sl + (bottom ? 1 : 0));
+            } else {
+                sample = sample_sequences(seqs, sn, sl, bottom, seed, n_sampled, row_len); // :867
+            }
             if (mr_v > 0) print("Sampled " + std::to_string(n_sampled) + " sequences", 1);
 
-            int st = apc_upload_sample(ctx0, sample.data(), n_sampled, row_len);
+            if (!device_ingest) st = apc_upload_sample(ctx0, sample.data(), n_sampled, row_len);
             if (st != APC_OK) return gpu_fail("uploading the sample", ctx0, st);
 
             if (mr_v > 0) print("Exact k-mer count", tab_level); // :872-874

@@ -101,6 +101,15 @@ int apch_sample(const apch_reads *r, uint64_t nb_sample, uint64_t cut, int bot, 
     )
 }
 
+int apch_shuffle_order(uint64_t n, int64_t seed, uint32_t *out) {
+    APCH_GUARD(-1,
+    if (!out && n) return -1;
+    const std::vector<int> v = apch::shuffle_order(n, seed);
+    for (uint64_t i = 0; i < n; i++) out[i] = (uint32_t)v[i];
+    return 0;
+    )
+}
+
 int apch_synth_ends(uint64_t seed, uint64_t first, uint64_t n, uint32_t sl, int bot, uint8_t *out) {
     APCH_GUARD(-1,
     if (!out && n) return -1;

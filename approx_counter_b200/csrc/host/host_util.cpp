@@ -542,9 +542,7 @@ bool read_fastx(const std::string &path, Reads &out, std::string &err) {
 }
 
 // ---- sampling --------------------------------------------------------------------
-std::vector<uint8_t> sample_sequences(const Reads &reads, uint64_t nb_sample, uint64_t cut, bool bot,
-                                      int64_t seed, uint64_t &n_sampled, uint32_t &row_len) { // :415-476
-    const uint64_t n = reads.size();
+std::vector<int> shuffle_order(uint64_t n, int64_t seed) { // :423-429
     std::vector<int> vec(n);
     std::iota(vec.begin(), vec.end(), 0);
     std::mt19937 g;
@@ -555,6 +553,13 @@ std::vector<uint8_t> sample_sequences(const Reads &reads, uint64_t nb_sample, ui
         g.seed((uint32_t)seed);
     }
     std::shuffle(vec.begin(), vec.end(), g); // :429
+    return vec;
+}
+
+std::vector<uint8_t> sample_sequences(const Reads &reads, uint64_t nb_sample, uint64_t cut, bool bot,
+                                      int64_t seed, uint64_t &n_sampled, uint32_t &row_len) { // :415-476
+    const uint64_t n = reads.size();
+    const std::vector<int> vec = shuffle_order(n, seed);
     row_len = (uint32_t)(cut + (bot ? 1 : 0));
     // the walk of :447-471 only needs the read lengths; the copies are done afterwards, in parallel
     std::vector<uint64_t> chosen;

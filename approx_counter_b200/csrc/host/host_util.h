@@ -60,6 +60,7 @@ struct Reads {
 bool read_fastx(const std::string &path, Reads &out, std::string &err);
 
 // :415-476.  Returns the ASCII sample matrix (n_sampled rows of cut [+1 if bot]).
+std::vector<int> shuffle_order(uint64_t n, int64_t seed); // :423-429
 std::vector<uint8_t> sample_sequences(const Reads &reads, uint64_t nb_sample, uint64_t cut, bool bot,
                                       int64_t seed, uint64_t &n_sampled, uint32_t &row_len);
 

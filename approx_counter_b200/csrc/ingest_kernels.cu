@@ -1,0 +1,251 @@
+// ingest_kernels.cu — K6: FASTA / FASTQ ingest and read sampling on the device.
+//
+// Replaces, for inputs whose records keep their sequence on ONE line (single-line FASTA, 4-line FASTQ — what
+// basecallers write), the reference's readRecords (:819-825) and the walk and copies of sampleSequences
+// (:447-471): the file's bytes are copied to HBM once, the records are indexed there, and every sample (start
+// and end of a run, every run of -mr) is gathered from the resident bytes straight into the staging buffer the
+// layout kernels read — no host parse, no host-side copies of the read ends, no second upload.
+//
+//   count_newlines_kernel   one pass over the bytes: newlines per 16 KB tile            (HBM-bound: reads 1 B / B)
+//   [prefix sum over the tiles: cub::DeviceScan, tiles = bytes / 16384 elements]
+//   write_newlines_kernel   second pass: the byte offset of every newline, ascending    (reads 1 B / B, L2-warm for
+//                                                                                         files below ~100 MB)
+//   index_records_kernel    one warp per record: grammar check (header / '+' markers, quality length, no blanks
+//                           inside the sequence) and the record's (sequence offset, length)
+//   pick_*_kernel + prefix  the first nb_sample ids of the caller's shuffled order with length >= 2*cut (:447-461)
+//   gather_ends_kernel      prefix(cut) (:466) or the last cut+1 bases (:463) of the chosen reads -> ASCII rows
+//
+// Anything outside that grammar (wrapped sequences, blank lines between records, blanks inside a sequence) is
+// reported as APC_ERR_FORMAT by apc_ingest_fastx and is the host parser's job (csrc/host/host_util.cpp).
+#include <cub/device/device_scan.cuh>
+
+#include "apc_internal.h"
+
+namespace apc {
+
+constexpr int kIngestThreads = 256;
+constexpr int kIngestIters = (int)(kIngestTileBytes / (kIngestThreads * 16)); // uint4 loads per thread and tile
+static_assert(kIngestIters * kIngestThreads * 16 == (int)kIngestTileBytes, "tile = threads x iterations x 16 bytes");
+
+// bit b of the result = byte b of the 16 is '\n'
+__device__ __forceinline__ uint32_t newline_mask16(const uint4 v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t eq = __vcmpeq4(w[i], 0x0A0A0A0Au) & 0x08040201u; // byte j -> bit 9 j
+        eq = (eq | (eq >> 8) | (eq >> 16) | (eq >> 24)) & 0xFu;   // -> bit j
+        m |= eq << (4 * i);
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(kIngestThreads)
+count_newlines_kernel(const uint4 *__restrict__ file, const uint64_t n_tiles, uint64_t *__restrict__ tile_nl) {
+    __shared__ uint32_t s_warp[kIngestThreads / 32];
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint4 *p = file + tile * (kIngestTileBytes / 16) + threadIdx.x;
+        uint4 v[kIngestIters];
+#pragma unroll
+        for (int it = 0; it < kIngestIters; it++) v[it] = __ldg(p + it * kIngestThreads);
+        uint32_t c = 0;
+#pragma unroll
+        for (int it = 0; it < kIngestIters; it++) c += __popc(newline_mask16(v[it]));
+        c = __reduce_add_sync(0xFFFFFFFFu, c);
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < kIngestThreads / 32; w++) t += s_warp[w];
+            tile_nl[tile] = t;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kIngestThreads)
+write_newlines_kernel(const uint4 *__restrict__ file, const uint64_t n_tiles, const uint64_t *__restrict__ tile_base,
+                      uint64_t *__restrict__ nl) {
+    __shared__ uint32_t s_warp[kIngestThreads / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint4 *p = file + tile * (kIngestTileBytes / 16) + threadIdx.x;
+        uint4 v[kIngestIters];
+#pragma unroll
+        for (int it = 0; it < kIngestIters; it++) v[it] = __ldg(p + it * kIngestThreads);
+        uint64_t base = tile_base[tile];
+#pragma unroll
+        for (int it = 0; it < kIngestIters; it++) {
+            uint32_t m = newline_mask16(v[it]);
+            const uint32_t c = __popc(m);
+            uint32_t incl = c; // inclusive prefix over the warp
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (uint32_t)d) incl += o;
+            }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kIngestThreads / 32; w++) {
+                const uint32_t t = s_warp[w];
+                before += (uint32_t)w < warp ? t : 0;
+                total += t;
+            }
+            uint64_t at = base + before + incl - c;
+            const uint64_t byte0 = tile * kIngestTileBytes + ((uint64_t)it * kIngestThreads + threadIdx.x) * 16;
+            while (m) {
+                nl[at++] = byte0 + (uint32_t)(__ffs((int)m) - 1);
+                m &= m - 1;
+            }
+            base += total;
+            __syncthreads();
+        }
+    }
+}
+
+struct LineTable {
+    const uint8_t *file;
+    const uint64_t *nl;
+    uint64_t n_nl, n_bytes; // line i = [i ? nl[i-1] + 1 : 0, i < n_nl ? nl[i] : n_bytes); n_nl + 1 lines
+    __device__ __forceinline__ uint64_t begin(uint64_t i) const { return i ? nl[i - 1] + 1 : 0; }
+    __device__ __forceinline__ uint64_t end(uint64_t i) const { return i < n_nl ? nl[i] : n_bytes; }
+};
+
+__device__ __forceinline__ bool is_blank(uint8_t ch) { return ch == ' ' || ch == '\t' || ch == '\r'; }
+
+constexpr int kIndexWarps = 8;
+
+// One warp per record.  FASTA: lines 2r (header, '>') and 2r+1 (sequence).  FASTQ: lines 4r ('@' header), 4r+1
+// (sequence), 4r+2 ('+'), 4r+3 (quality, as long as the sequence).  Trailing CR / blanks of the sequence line are
+// dropped like the host parser does; blanks inside it, or any other arrangement of lines, raise the flag.
+template <bool FASTQ>
+__global__ void __launch_bounds__(kIndexWarps * 32)
+index_records_kernel(const LineTable t, const uint64_t n_records, uint64_t *__restrict__ rec_start,
+                     uint32_t *__restrict__ rec_len, uint32_t *__restrict__ flag) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t r = (uint64_t)blockIdx.x * kIndexWarps + (threadIdx.x >> 5);
+    if (r >= n_records) return;
+    const uint64_t l0 = r * (FASTQ ? 4 : 2);
+    bool bad = t.file[t.begin(l0)] != (FASTQ ? '@' : '>'); // an empty header line reads its own '\n' here
+    const uint64_t sb = t.begin(l0 + 1);
+    uint64_t se = t.end(l0 + 1);
+    while (se > sb && is_blank(t.file[se - 1])) se--;
+    if (se > sb) bad |= t.file[sb] == (FASTQ ? '+' : '>');
+    for (uint64_t pos = sb + lane; pos < se; pos += 32) bad |= is_blank(t.file[pos]);
+    if (FASTQ) {
+        bad |= t.file[t.begin(l0 + 2)] != '+';
+        const uint64_t qb = t.begin(l0 + 3);
+        uint64_t qe = t.end(l0 + 3);
+        while (qe > qb && t.file[qe - 1] == '\r') qe--;
+        bad |= (qe - qb) != (se - sb);
+    }
+    bad |= (se - sb) > 0xFFFFFFFFull;
+    bad = __any_sync(0xFFFFFFFFu, bad);
+    if (lane == 0) {
+        rec_start[r] = sb;
+        rec_len[r] = (uint32_t)(se - sb);
+        if (bad) atomicOr(flag, 1u);
+    }
+}
+
+// :447-461 — position i of the (shuffled) order is taken when its read has at least 2 * cut bases
+__global__ void pick_flag_kernel(const uint32_t *__restrict__ order, const uint64_t n, const uint32_t *__restrict__ rec_len,
+                                 const uint64_t min_len, uint32_t *__restrict__ flags, uint32_t *__restrict__ flag) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t id = order ? order[i] : i;
+    if (id >= n) { // not a permutation of 0..n-1
+        atomicOr(flag, 2u);
+        flags[i] = 0;
+        return;
+    }
+    flags[i] = rec_len[id] >= min_len ? 1u : 0u;
+}
+
+__global__ void pick_choose_kernel(const uint32_t *__restrict__ order, const uint64_t n, const uint32_t *__restrict__ flags,
+                                   const uint32_t *__restrict__ pos, const uint64_t nb_sample, uint32_t *__restrict__ chosen) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (flags[i] && pos[i] < nb_sample) chosen[pos[i]] = order ? order[i] : (uint32_t)i;
+}
+
+// row j of the sample = prefix(seq, cut) (:466) or suffix(seq, len - 1 - cut) (:463: cut + 1 bases) of read chosen[j]
+__global__ void gather_ends_kernel(const uint8_t *__restrict__ file, const uint64_t *__restrict__ rec_start,
+                                   const uint32_t *__restrict__ rec_len, const uint32_t *__restrict__ chosen,
+                                   const uint64_t n_bytes_out, const uint32_t row_len, const uint32_t cut, const bool bot,
+                                   uint8_t *__restrict__ stage) {
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_bytes_out) return;
+    const uint64_t j = idx / row_len;
+    const uint32_t o = (uint32_t)(idx - j * row_len);
+    const uint32_t id = chosen[j];
+    const uint64_t from = rec_start[id] + (bot ? (uint64_t)rec_len[id] - 1 - cut : 0);
+    stage[idx] = file[from + o];
+}
+
+static unsigned grid_for(uint64_t items, int per_block) {
+    return (unsigned)std::min<uint64_t>((items + per_block - 1) / per_block, 0x7FFFFFFFull);
+}
+
+cudaError_t launch_count_newlines(const uint8_t *d_file, uint64_t n_tiles, uint64_t *d_tile_nl, cudaStream_t s) {
+    if (!n_tiles) return cudaSuccess;
+    count_newlines_kernel<<<grid_for(n_tiles, 1), kIngestThreads, 0, s>>>(reinterpret_cast<const uint4 *>(d_file), n_tiles,
+                                                                         d_tile_nl);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_write_newlines(const uint8_t *d_file, uint64_t n_tiles, const uint64_t *d_tile_base, uint64_t *d_nl,
+                                  cudaStream_t s) {
+    if (!n_tiles) return cudaSuccess;
+    write_newlines_kernel<<<grid_for(n_tiles, 1), kIngestThreads, 0, s>>>(reinterpret_cast<const uint4 *>(d_file), n_tiles,
+                                                                         d_tile_base, d_nl);
+    return cudaGetLastError();
+}
+
+// exclusive prefix sums (in place for the u64 form); d_temp == nullptr: only the temp size is returned
+cudaError_t ingest_prefix_u64(void *d_temp, size_t &temp_bytes, uint64_t *d_inout, uint64_t n, cudaStream_t s) {
+    return cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_inout, d_inout, (int64_t)n, s);
+}
+
+cudaError_t ingest_prefix_u32(void *d_temp, size_t &temp_bytes, const uint32_t *d_in, uint32_t *d_out, uint64_t n,
+                              cudaStream_t s) {
+    return cub::DeviceScan::ExclusiveSum(d_temp, temp_bytes, d_in, d_out, (int64_t)n, s);
+}
+
+cudaError_t launch_index_records(const uint8_t *d_file, const uint64_t *d_nl, uint64_t n_nl, uint64_t n_bytes, bool fastq,
+                                 uint64_t n_records, uint64_t *d_rec_start, uint32_t *d_rec_len, uint32_t *d_flag,
+                                 cudaStream_t s) {
+    if (!n_records) return cudaSuccess;
+    const LineTable t{d_file, d_nl, n_nl, n_bytes};
+    const unsigned grid = grid_for(n_records, kIndexWarps);
+    if (fastq) index_records_kernel<true><<<grid, kIndexWarps * 32, 0, s>>>(t, n_records, d_rec_start, d_rec_len, d_flag);
+    else index_records_kernel<false><<<grid, kIndexWarps * 32, 0, s>>>(t, n_records, d_rec_start, d_rec_len, d_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pick_reads(const uint32_t *d_order, uint64_t n, const uint32_t *d_rec_len, uint64_t min_len,
+                              uint64_t nb_sample, uint32_t *d_flags, uint32_t *d_pos, uint32_t *d_chosen, void *d_temp,
+                              size_t temp_bytes, uint32_t *d_flag, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    pick_flag_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_order, n, d_rec_len, min_len, d_flags, d_flag);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if ((e = ingest_prefix_u32(d_temp, temp_bytes, d_flags, d_pos, n, s)) != cudaSuccess) return e;
+    pick_choose_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_order, n, d_flags, d_pos, nb_sample, d_chosen);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_ends(const uint8_t *d_file, const uint64_t *d_rec_start, const uint32_t *d_rec_len,
+                               const uint32_t *d_chosen, uint64_t n_sampled, uint32_t row_len, uint32_t cut, bool bot,
+                               uint8_t *d_stage, cudaStream_t s) {
+    const uint64_t n_out = n_sampled * row_len;
+    if (!n_out) return cudaSuccess;
+    gather_ends_kernel<<<grid_for(n_out, 256), 256, 0, s>>>(d_file, d_rec_start, d_rec_len, d_chosen, n_out, row_len, cut,
+                                                          bot, d_stage);
+    return cudaGetLastError();
+}
+
+} // namespace apc

@@ -27,6 +27,7 @@ HOST_SYMBOLS = {
     "apch_reads_mapped": (C.c_int, [_vp]),
     "apch_reads_free": (None, [_vp]),
     "apch_sample": (C.c_int, [_vp, C.c_uint64, C.c_uint64, C.c_int, C.c_int64, _vp, _u64p]),
+    "apch_shuffle_order": (C.c_int, [C.c_uint64, C.c_int64, _vp]),
     "apch_synth_ends": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, _vp]),
     "apch_synth_write": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int]),
     "apch_cli_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
@@ -137,6 +138,14 @@ class Reads:
             self.close()
         except Exception:
             pass
+
+
+def shuffle_order(n, seed=-1):
+    """The shuffled read ids of sampleSequences (:423-429): uint32[n]."""
+    out = np.zeros(int(n), np.uint32)
+    if lib().apch_shuffle_order(int(n), int(seed), out.ctypes.data) != 0:
+        raise MemoryError("apch_shuffle_order")
+    return out
 
 
 def synth_ends(seed, first, n, sl, bot, out=None):

@@ -38,6 +38,7 @@ extern "C" {
 #define APC_ERR_NOMEM (-6)      /* host or device allocation failed */
 #define APC_ERR_CAPACITY (-7)   /* caller-provided output capacity too small */
 #define APC_ERR_COMM (-8)       /* NCCL unavailable or a collective failed; see apc_last_error */
+#define APC_ERR_FORMAT (-9)     /* apc_ingest_fastx: input outside the device parser's grammar */
 #define APC_MAXERR 2            /* compile-time edit bound, reference :25 */
 
 typedef struct apc_ctx apc_ctx;
@@ -99,6 +100,44 @@ int apc_upload_sample_ragged(apc_ctx *ctx, const uint8_t *bases,
                              const uint64_t *offsets, uint64_t n_reads);
 int apc_sample_info(const apc_ctx *ctx, uint64_t *n_reads, uint32_t *max_len,
                     uint64_t *total_bases);
+
+/* ---- ingest on the device: FASTA / FASTQ bytes -> sampled read ends -----------
+ * Replaces readRecords (:819-825) and the walk and copies of sampleSequences
+ * (:447-471) for inputs whose records keep their sequence on ONE line
+ * (single-line FASTA: '>' header, sequence; 4-line FASTQ: '@' header, sequence,
+ * '+' line, quality of the sequence's length; LF or CRLF; blank lines only at
+ * the end of the file): the file's bytes are copied to HBM once, the records
+ * are indexed there (newline index + one warp per record checking the grammar),
+ * and every sample is gathered from the resident bytes straight into the
+ * staging buffer of the layout kernels.  Any other input returns
+ * APC_ERR_FORMAT and belongs to the host parser (apch_reads_load), which takes
+ * wrapped records and stray blanks.  `file_bytes` is a HOST pointer (a read-only
+ * mapping of the file will do); it is not needed after the call returns. */
+int apc_ingest_fastx(apc_ctx *ctx, const uint8_t *file_bytes, uint64_t n_bytes,
+                     uint64_t *n_records_out, int *is_fastq_out);
+/* seqs[first .. first+n) lengths (`length(sequence_set[id])`, :461) of the
+ * resident file. */
+int apc_ingest_lengths(apc_ctx *ctx, uint64_t first, uint64_t n,
+                       uint32_t *lens_out);
+/* sampleSequences (:415-476) over the resident file: walks `order` (HOST, the
+ * shuffled read ids of :423-429 — apch_shuffle_order gives the reference's
+ * mt19937 + std::shuffle; NULL = 0, 1, 2, ...), takes the first nb_sample reads
+ * of length >= 2*cut (:447-461) and makes their first `cut` bases (bot == 0,
+ * :466) or last cut+1 bases (bot != 0, :463) the context's sample, exactly as
+ * apc_upload_sample would with the rows sampleSequences returns.  n_order must
+ * equal the record count.  Synchronises. */
+int apc_sample_resident(apc_ctx *ctx, const uint32_t *order, uint64_t n_order,
+                        uint64_t nb_sample, uint32_t cut, int bot,
+                        uint64_t *n_sampled_out);
+/* ASCII rows (n_reads x read_len, see apc_sample_info) of the resident sample
+ * as uploaded or gathered — what sampleSequences would have returned.  Not
+ * available after apc_upload_sample_ragged. */
+int apc_download_sample(apc_ctx *ctx, uint8_t *bases_out, uint64_t capacity);
+/* Device times of the last apc_ingest_fastx (H2D copy of the file; newline
+ * index + record index kernels) and apc_sample_resident (pick + gather +
+ * layout kernels), CUDA events, milliseconds.  Any pointer may be NULL. */
+int apc_ingest_timing(const apc_ctx *ctx, float *copy_ms, float *index_ms,
+                      float *sample_ms);
 
 /* ---- exact count + filter + top-N -------------------------------------------
  * Replaces count_kmers (:487-519, called :874) followed by get_most_frequent

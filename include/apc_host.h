@@ -59,6 +59,12 @@ void apch_reads_free(apch_reads *r);
 int apch_sample(const apch_reads *r, uint64_t nb_sample, uint64_t cut, int bot,
                 int64_t seed, uint8_t *out, uint64_t *n_sampled);
 
+/* :423-429 — the shuffled read ids alone: out[0..n) = 0..n-1 through
+ * std::shuffle over std::mt19937 seeded like apch_sample (seed < 0:
+ * std::random_device).  Feeds apc_sample_resident, which walks the ids on the
+ * device. */
+int apch_shuffle_order(uint64_t n, int64_t seed, uint32_t *out);
+
 /* Synthetic ONT-like reads with planted adapters: read i of
  * stream `seed` is a pure function of (seed, i, sl).  apch_synth_ends writes
  * the sampled ends of reads [first, first+n) directly (n rows of sl, or sl+1

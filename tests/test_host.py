@@ -271,3 +271,24 @@ def test_oracle_synth_equals_host_synth(host):
                                (1002 | 1 << 40, 0, 300, 100)):   # bit 40: adapter offsets uniform in 0..sl/2
         for bot in (False, True):
             assert np.array_equal(orc.synth_ends(seed, first, n, sl, bot), host.synth_ends(seed, first, n, sl, bot))
+
+
+def test_shuffle_order_is_the_samplers_order(built, tmp_path):
+    """apch_shuffle_order (:423-429) hands out the ids apch_sample walks: gathering by hand along it gives the
+    sampler's rows (this is what apc_sample_resident does on the device)."""
+    from approx_counter_b200 import host
+    rng = np.random.default_rng(3)
+    reads = [rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(rng.integers(0, 120))).tobytes() for _ in range(300)]
+    path = tmp_path / "r.fa"
+    path.write_bytes(b"".join(b">r%d\n%s\n" % (i, s) for i, s in enumerate(reads)))
+    r = host.Reads(path)
+    for seed in (0, 1, 99):
+        order = host.shuffle_order(len(reads), seed)
+        assert sorted(order.tolist()) == list(range(len(reads)))
+        assert np.array_equal(order, host.shuffle_order(len(reads), seed))
+        for cut, bot, sn in ((20, False, 50), (20, True, 1000), (35, True, 7)):
+            ids = [i for i in order if len(reads[i]) >= 2 * cut][:sn]
+            want = [reads[i][len(reads[i]) - 1 - cut:] if bot else reads[i][:cut] for i in ids]
+            got = r.sample(sn, cut, bot, seed)
+            assert [row.tobytes() for row in got] == want
+    assert len(host.shuffle_order(0, 1)) == 0
