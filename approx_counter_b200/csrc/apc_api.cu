@@ -179,6 +179,10 @@ void apc_destroy(apc_ctx *c) {
     cudaFree(c->d_pick);
     cudaFree(c->d_ingest_temp);
     cudaFree(c->d_ingest_flag);
+    for (int b = 0; b < 2; b++) {
+        if (c->h_file_stage[b]) cudaFreeHost(c->h_file_stage[b]);
+        if (c->ev_file_stage[b]) cudaEventDestroy(c->ev_file_stage[b]);
+    }
     for (auto &e : c->ev_ingest)
         if (e) cudaEventDestroy(e);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -320,10 +324,34 @@ int apc_ingest_fastx(apc_ctx *c, const uint8_t *file_bytes, uint64_t n_bytes, ui
     APC_CUDA(c, apc::ingest_prefix_u64(nullptr, temp_bytes, c->d_tile_nl, n_tiles + 1, c->stream));
     if ((st = apc::grow(c, c->d_ingest_temp, c->ingest_temp_cap, temp_bytes))) return st;
     APC_CUDA(c, cudaEventRecord(c->ev_ingest[0], c->stream));
-    // pageable memory is staged by the driver; pieces keep its staging buffers busy without a giant single request
-    for (uint64_t off = 0; off < n_eff; off += (uint64_t)64 << 20) {
-        const uint64_t len = std::min<uint64_t>((uint64_t)64 << 20, n_eff - off);
-        APC_CUDA(c, cudaMemcpyAsync(c->d_file + off, file_bytes + off, len, cudaMemcpyHostToDevice, c->stream));
+    if (c->opt_ingest_staging && n_eff >= 4 * apc::kIngestStageBytes) {
+        // two page-locked pieces in flight: the host threads fill one (apch::parallel_copy) while the copy engine
+        // drains the other — the driver's own staging of pageable memory is one thread deep (about 11 GB/s)
+        for (int b = 0; b < 2; b++) {
+            if (!c->h_file_stage[b]) {
+                cudaError_t e = cudaHostAlloc((void **)&c->h_file_stage[b], apc::kIngestStageBytes, cudaHostAllocDefault);
+                if (e != cudaSuccess) {
+                    c->h_file_stage[b] = nullptr;
+                    return apc::fail(c, APC_ERR_NOMEM, "cudaHostAlloc (file staging)", e);
+                }
+            }
+            if (!c->ev_file_stage[b]) APC_CUDA(c, cudaEventCreateWithFlags(&c->ev_file_stage[b], cudaEventDisableTiming));
+        }
+        uint64_t piece = 0;
+        for (uint64_t off = 0; off < n_eff; off += apc::kIngestStageBytes, piece++) {
+            const uint64_t len = std::min<uint64_t>(apc::kIngestStageBytes, n_eff - off);
+            const int b = (int)(piece & 1);
+            if (piece >= 2) APC_CUDA(c, cudaEventSynchronize(c->ev_file_stage[b]));
+            apch::parallel_copy(c->h_file_stage[b], file_bytes + off, (size_t)len);
+            APC_CUDA(c, cudaMemcpyAsync(c->d_file + off, c->h_file_stage[b], len, cudaMemcpyHostToDevice, c->stream));
+            APC_CUDA(c, cudaEventRecord(c->ev_file_stage[b], c->stream));
+        }
+    } else {
+        // small files: pageable memory, staged by the driver
+        for (uint64_t off = 0; off < n_eff; off += (uint64_t)64 << 20) {
+            const uint64_t len = std::min<uint64_t>((uint64_t)64 << 20, n_eff - off);
+            APC_CUDA(c, cudaMemcpyAsync(c->d_file + off, file_bytes + off, len, cudaMemcpyHostToDevice, c->stream));
+        }
     }
     if (padded > n_eff) APC_CUDA(c, cudaMemsetAsync(c->d_file + n_eff, 0, padded - n_eff, c->stream));
     APC_CUDA(c, cudaEventRecord(c->ev_ingest[1], c->stream));
@@ -820,6 +848,10 @@ int apc_set_option(apc_ctx *c, const char *name, int64_t value) {
     c->plan_gen++; // any option may change what a scan launches
     if (!std::strcmp(name, "scan_graph")) {
         c->opt_graph = value != 0;
+        return APC_OK;
+    }
+    if (!std::strcmp(name, "ingest_staging")) {
+        c->opt_ingest_staging = value != 0;
         return APC_OK;
     }
     if (!std::strcmp(name, "scan_variant")) {

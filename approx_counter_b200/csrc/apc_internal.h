@@ -190,6 +190,9 @@ struct Ctx {
     size_t rec_len_cap = 0;
     uint32_t *d_pick = nullptr;      // sampling scratch: order | eligible flags | their prefix sum | chosen ids, n u32 each
     size_t pick_cap = 0;
+    uint8_t *h_file_stage[2] = {nullptr, nullptr}; // page-locked staging of the file copy (two pieces in flight)
+    cudaEvent_t ev_file_stage[2] = {};
+    int opt_ingest_staging = 1;      // 0: hand the caller's (pageable) buffer to cudaMemcpyAsync directly
     void *d_ingest_temp = nullptr;   // cub temp storage of the two prefix sums
     size_t ingest_temp_cap = 0;
     uint32_t *d_ingest_flag = nullptr; // [0] malformed input seen by a kernel
@@ -237,6 +240,7 @@ cudaError_t launch_build_tiles_ragged(const uint8_t *d_ascii, const uint64_t *d_
 
 // ingest_kernels.cu
 constexpr uint64_t kIngestTileBytes = 16384;
+constexpr uint64_t kIngestStageBytes = (uint64_t)16 << 20; // one staging piece of the file copy
 cudaError_t launch_count_newlines(const uint8_t *d_file, uint64_t n_tiles, uint64_t *d_tile_nl, cudaStream_t s);
 cudaError_t launch_write_newlines(const uint8_t *d_file, uint64_t n_tiles, const uint64_t *d_tile_base, uint64_t *d_nl,
                                   cudaStream_t s);
@@ -281,5 +285,10 @@ cudaError_t measure_int_peak(const Ctx &c, double *lop3, double *imad, double *m
 cudaError_t microbench(const Ctx &c, const char *name, double *value);
 
 } // namespace apc
+
+// host/host_util.cpp: memcpy split over the host threads (OpenMP)
+namespace apch {
+void parallel_copy(void *dst, const void *src, size_t n);
+}
 
 struct apc_ctx : public apc::Ctx {};

@@ -98,8 +98,9 @@ const OptSpec OPTIONS[] = {
     {"", "gpus", Kind::Int, "[extension] number of GPUs to shard the sampled reads over (default 1)"},
     {"", "device", Kind::Int, "[extension] first CUDA device to use (default 0)"},
     {"", "ingest", Kind::String,
-     "[extension] host (default): the input is parsed and sampled by host threads; device: its bytes are copied to the "
-     "GPU, indexed and sampled there (single-line FASTA / 4-line FASTQ, one GPU; anything else falls back to host)"},
+     "[extension] device (default): the input's bytes are copied to the GPU, indexed and sampled there (single-line "
+     "FASTA / 4-line FASTQ on one GPU; anything else is handed to the host parser); host: parsed and sampled by host "
+     "threads"},
     {"", "version-check", Kind::String, "[accepted for SeqAn compatibility, ignored]"},
 };
 
@@ -216,7 +217,7 @@ int cli_main(int argc, const char **argv) {
     float lc = 1.0;
     uint64_t n_gpus = 1, device0 = 0;
     int64_t seed = -1;
-    std::string ingest = "host";
+    std::string ingest = "device";
 
     get_str(parser, "config", config_file);
     if (!config_file.empty()) { // :721-737
@@ -337,6 +338,9 @@ int cli_main(int argc, const char **argv) {
         if (v > 1) print("File mapped; waiting for the CUDA context", tab_level);
         creator.join();
         if (create_status != APC_OK) return gpu_fail("cannot open CUDA device", nullptr, create_status);
+        if (v > 1)
+            print("CUDA context ready (beside the mapping: context " + std::to_string(create_ms) + " ms, buffers and kernels " +
+                      std::to_string(reserve_ms) + " ms); copying the input to the GPU", tab_level);
         int is_fastq = 0;
         const int st = apc_ingest_fastx(gpus[0].ctx, file.data, file.size, &n_seqs, &is_fastq);
         if (st == APC_OK) {

@@ -541,6 +541,18 @@ bool read_fastx(const std::string &path, Reads &out, std::string &err) {
     return true;
 }
 
+// memcpy split over the host threads: one thread moves about 10 GB/s out of a file mapping (page-cache pages are
+// mapped on first touch), the copy engine takes five times that from page-locked memory (apc_ingest_fastx)
+void parallel_copy(void *dst, const void *src, size_t n) {
+    const size_t piece = (size_t)1 << 20;
+    const int64_t pieces = (int64_t)((n + piece - 1) / piece);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < pieces; i++) {
+        const size_t off = (size_t)i * piece;
+        memcpy((char *)dst + off, (const char *)src + off, std::min(piece, n - off));
+    }
+}
+
 // ---- sampling --------------------------------------------------------------------
 std::vector<int> shuffle_order(uint64_t n, int64_t seed) { // :423-429
     std::vector<int> vec(n);

@@ -116,6 +116,19 @@ struct LineTable {
 
 __device__ __forceinline__ bool is_blank(uint8_t ch) { return ch == ' ' || ch == '\t' || ch == '\r'; }
 
+// bit b of the result = byte b of the 16 is a blank (' ', TAB or CR)
+__device__ __forceinline__ uint32_t blank_mask16(const uint4 v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t eq = (__vcmpeq4(w[i], 0x20202020u) | __vcmpeq4(w[i], 0x09090909u) | __vcmpeq4(w[i], 0x0D0D0D0Du)) & 0x08040201u;
+        eq = (eq | (eq >> 8) | (eq >> 16) | (eq >> 24)) & 0xFu;
+        m |= eq << (4 * i);
+    }
+    return m;
+}
+
 constexpr int kIndexWarps = 8;
 
 // One warp per record.  FASTA: lines 2r (header, '>') and 2r+1 (sequence).  FASTQ: lines 4r ('@' header), 4r+1
@@ -134,7 +147,15 @@ index_records_kernel(const LineTable t, const uint64_t n_records, uint64_t *__re
     uint64_t se = t.end(l0 + 1);
     while (se > sb && is_blank(t.file[se - 1])) se--;
     if (se > sb) bad |= t.file[sb] == (FASTQ ? '+' : '>');
-    for (uint64_t pos = sb + lane; pos < se; pos += 32) bad |= is_blank(t.file[pos]);
+    // blanks inside the sequence: the line is read as aligned 16-byte pieces (the file buffer is 256-byte aligned and
+    // padded to whole tiles), one per lane and step, bytes outside [sb, se) masked out
+    for (uint64_t at = (sb & ~(uint64_t)15) + 16 * lane; at < se; at += 16 * 32) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(t.file + at));
+        uint32_t m = blank_mask16(v);
+        if (at < sb) m &= 0xFFFFu << (uint32_t)(sb - at);
+        if (at + 16 > se) m &= 0xFFFFu >> (uint32_t)(at + 16 - se);
+        bad |= m != 0;
+    }
     if (FASTQ) {
         bad |= t.file[t.begin(l0 + 2)] != '+';
         const uint64_t qb = t.begin(l0 + 3);
@@ -172,18 +193,38 @@ __global__ void pick_choose_kernel(const uint32_t *__restrict__ order, const uin
     if (flags[i] && pos[i] < nb_sample) chosen[pos[i]] = order ? order[i] : (uint32_t)i;
 }
 
-// row j of the sample = prefix(seq, cut) (:466) or suffix(seq, len - 1 - cut) (:463: cut + 1 bases) of read chosen[j]
+// row j of the sample = prefix(seq, cut) (:466) or suffix(seq, len - 1 - cut) (:463: cut + 1 bases) of read chosen[j].
+// One thread fills 16 consecutive bytes of the row-major sample (one 128-bit store; they may straddle two rows).
 __global__ void gather_ends_kernel(const uint8_t *__restrict__ file, const uint64_t *__restrict__ rec_start,
                                    const uint32_t *__restrict__ rec_len, const uint32_t *__restrict__ chosen,
                                    const uint64_t n_bytes_out, const uint32_t row_len, const uint32_t cut, const bool bot,
                                    uint8_t *__restrict__ stage) {
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t idx = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (idx >= n_bytes_out) return;
-    const uint64_t j = idx / row_len;
-    const uint32_t o = (uint32_t)(idx - j * row_len);
-    const uint32_t id = chosen[j];
-    const uint64_t from = rec_start[id] + (bot ? (uint64_t)rec_len[id] - 1 - cut : 0);
-    stage[idx] = file[from + o];
+    uint64_t j = idx / row_len;
+    uint32_t o = (uint32_t)(idx - j * row_len);
+    uint32_t id = chosen[j];
+    const uint8_t *src = file + rec_start[id] + (bot ? (uint64_t)rec_len[id] - 1 - cut : 0);
+    const uint32_t n = (uint32_t)min((uint64_t)16, n_bytes_out - idx);
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (uint32_t b = 0; b < 16; b++) {
+        if (b < n) {
+            w[b >> 2] |= (uint32_t)src[o] << (8 * (b & 3));
+            if (++o == row_len && b + 1 < n) { // next row
+                o = 0;
+                id = chosen[++j];
+                src = file + rec_start[id] + (bot ? (uint64_t)rec_len[id] - 1 - cut : 0);
+            }
+        }
+    }
+    if (n == 16) {
+        *reinterpret_cast<uint4 *>(stage + idx) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+#pragma unroll
+        for (uint32_t b = 0; b < 16; b++)
+            if (b < n) stage[idx + b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+    }
 }
 
 static unsigned grid_for(uint64_t items, int per_block) {
@@ -243,7 +284,7 @@ cudaError_t launch_gather_ends(const uint8_t *d_file, const uint64_t *d_rec_star
                                uint8_t *d_stage, cudaStream_t s) {
     const uint64_t n_out = n_sampled * row_len;
     if (!n_out) return cudaSuccess;
-    gather_ends_kernel<<<grid_for(n_out, 256), 256, 0, s>>>(d_file, d_rec_start, d_rec_len, d_chosen, n_out, row_len, cut,
+    gather_ends_kernel<<<grid_for((n_out + 15) / 16, 256), 256, 0, s>>>(d_file, d_rec_start, d_rec_len, d_chosen, n_out, row_len, cut,
                                                           bot, d_stage);
     return cudaGetLastError();
 }

@@ -257,7 +257,10 @@ uint64_t apc_last_scan_launches(const apc_ctx *ctx);
  * graph and replayed from then on (one launch instead of up to 13 + fork/join
  * events), 0 (default) = always launch directly — back-to-back scans hide the
  * launches behind the previous scan anyway, and the graph's node dependencies
- * cost about what it saves (DESIGN.md tuning log). */
+ * cost about what it saves (DESIGN.md tuning log).  "ingest_staging": 1
+ * (default) = apc_ingest_fastx copies files of 64 MB and more through two
+ * page-locked 16 MB pieces filled by the host threads, 0 = hands the caller's
+ * buffer to cudaMemcpyAsync as it is. */
 int apc_set_option(apc_ctx *ctx, const char *name, int64_t value);
 
 /* The scan plan apc_set_queries would build for these k-mers (needs no GPU):

@@ -50,14 +50,17 @@ def test_binary_matches_oracle_files(built, tmp_path, fastq, k, sl, lim, n):
     reads = [r.seq(i) for i in range(len(r))]
     assert len(reads) == n
     out, exact = tmp_path / "out.txt", tmp_path / "exact.txt"
-    p = subprocess.run([BIN, "-k", str(k), "-sn", str(n), "-sl", str(sl), "-lim", str(lim), "-lc", "1.0",
-                        "-e", str(exact), "-o", str(out), "-nt", "4", str(path)],
-                       capture_output=True, text=True, timeout=300)
-    assert p.returncode == 0, p.stderr
     want = oracle_files(reads, k, sl, lim, 1.0, tmp_path)
-    for which in ("start", "end"):
-        assert (tmp_path / f"exact.txt_0.{which}").read_bytes() == want[which][0]   # `_<run>` always appended (:837)
-        assert (tmp_path / f"out.txt_0.{which}").read_bytes() == want[which][1]
+    # the input parsed and sampled on the GPU (the default) and by the host threads
+    for ingest in ("host", "device"):
+        p = subprocess.run([BIN, "-k", str(k), "-sn", str(n), "-sl", str(sl), "-lim", str(lim), "-lc", "1.0",
+                            "-e", str(exact), "-o", str(out), "-nt", "4", "-v", "2", "--ingest", ingest, str(path)],
+                           capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr
+        assert ("indexed on the GPU" in p.stdout) == (ingest == "device")
+        for which in ("start", "end"):
+            assert (tmp_path / f"exact.txt_0.{which}").read_bytes() == want[which][0]   # `_<run>` always appended (:837)
+            assert (tmp_path / f"out.txt_0.{which}").read_bytes() == want[which][1]
     lines = (tmp_path / "out.txt_0.start").read_text().splitlines()
     assert len(lines) == lim and all(len(x.split("\t")[0]) == k for x in lines)
     assert "Kmer size:" in p.stdout and "Approximate k-mer count" in p.stdout

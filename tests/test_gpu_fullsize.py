@@ -36,6 +36,9 @@ CONFIGS = {
     "C5": (1_000_000, 100, 16, 5000, 2003, False),   # one point of the sweep: -sn 1M -lim 5000
 }
 SLOW = {"C3", "C4", "C5"}
+# the binary parses and samples its input on the GPU by default (--ingest device, apc_ingest_fastx); C2 and C3 (FASTQ)
+# are also run with the host parser and sampler
+CASES = [(name, "device") for name in CONFIGS] + [("C2", "host"), ("C3", "host")]
 
 
 def oracle_end_files(sample, k, lim, tmp, which, threads):
@@ -54,8 +57,8 @@ def oracle_end_files(sample, k, lim, tmp, which, threads):
     return e.read_bytes(), o.read_bytes()
 
 
-@pytest.mark.parametrize("name", list(CONFIGS))
-def test_files_match_oracle_at_full_size(built, tmp_path, name):
+@pytest.mark.parametrize("name,ingest", CASES)
+def test_files_match_oracle_at_full_size(built, tmp_path, name, ingest):
     if name in SLOW and os.environ.get("APC_RUN_SLOW") != "1":
         pytest.skip(f"{name} at full size needs minutes of CPU time for the oracle: set APC_RUN_SLOW=1 "
                     "(tools/fullsize_slow.sh; last log in profiles/)")
@@ -66,9 +69,10 @@ def test_files_match_oracle_at_full_size(built, tmp_path, name):
     t0 = time.perf_counter()
     p = subprocess.run([BIN, "-k", str(k), "-sn", str(n), "-sl", str(sl), "-lim", str(lim), "-lc", "1.0",
                         "-e", str(tmp_path / "exact.txt"), "-o", str(tmp_path / "out.txt"), "-nt", "4", "-v", "2",
-                        str(path)], capture_output=True, text=True, timeout=1800)
+                        "--ingest", ingest, str(path)], capture_output=True, text=True, timeout=1800)
     t_bin = time.perf_counter() - t0
     assert p.returncode == 0, p.stderr
+    assert ("indexed on the GPU" in p.stdout) == (ingest == "device")
     os.unlink(path)
     t0 = time.perf_counter()
     for which, bot in (("start", False), ("end", True)):
@@ -78,5 +82,5 @@ def test_files_match_oracle_at_full_size(built, tmp_path, name):
         assert got_exact == want_exact, f"{name} {which}: exact top-{lim} file differs"
         assert got_out == want_out, f"{name} {which}: approximate count file differs"
         assert got_out.count(b"\n") == lim
-    print(f"\n[fullsize] {name}: n={n} sl={sl} k={k} lim={lim} fastq={fastq}: 4 files byte-identical; "
+    print(f"\n[fullsize] {name} (--ingest {ingest}): n={n} sl={sl} k={k} lim={lim} fastq={fastq}: 4 files byte-identical; "
           f"binary {t_bin:.2f} s wall, oracle {time.perf_counter() - t0:.1f} s")

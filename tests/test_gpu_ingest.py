@@ -188,3 +188,27 @@ def test_binary_device_ingest_writes_the_same_files(built, tmp_path, fastq, k, s
         assert p.returncode == 0, p.stderr
         assert "using the host parser" in p.stdout
         assert [(tmp_path / f"{x}_w_0.{w}").read_bytes() for x in "eo" for w in ("start", "end")] == files["host"]
+
+
+def test_staged_copy_of_a_large_file(built, counter, tmp_path):
+    """Files of 64 MB and more travel through the two page-locked staging pieces (several pieces, a ragged last
+    one): same records and samples as the host route, with and without the staging."""
+    from approx_counter_b200 import host
+    n, sl = 150_000, 150
+    path = tmp_path / "big.fa"
+    host.synth_write(path, 31337, n, sl)
+    assert os.path.getsize(path) > 4 * (16 << 20)
+    data = np.fromfile(path, np.uint8)
+    r, lens = host_view(path)
+    order = host.shuffle_order(n, 3)
+    want = {bot: r.sample(n // 3, sl, bot, 3) for bot in (False, True)}
+    try:
+        for staging in (1, 0):
+            counter.set_option("ingest_staging", staging)
+            assert counter.ingest_fastx(data) == (n, False)
+            assert np.array_equal(counter.ingest_lengths(), lens)
+            for bot in (False, True):
+                assert counter.sample_resident(n // 3, sl, bot, order) == n // 3
+                assert np.array_equal(counter.download_sample(), want[bot])
+    finally:
+        counter.set_option("ingest_staging", 1)

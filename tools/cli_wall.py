@@ -1,6 +1,6 @@
 """Wall-clock breakdown of the one-shot drop-in binary on the BASELINE configurations (phase timestamps of -v 2).
 
-    python tools/cli_wall.py [C1 C2 C3 C4] > gpurun_out/r02_cli_wall.md
+    python tools/cli_wall.py [--ingest device] [C1 C2 C3 C4] > gpurun_out/r02_cli_wall.md
 
 Every configuration is run twice (the second run has the input file in the page cache and the CUDA driver warm);
 the table reports the second run: process wall clock, then where it went."""
@@ -15,6 +15,13 @@ FASTQ = {"C3"}
 os.makedirs("/tmp/apc_cli", exist_ok=True)
 
 
+EXTRA = []
+if "--ingest" in sys.argv:
+    i = sys.argv.index("--ingest")
+    EXTRA = ["--ingest", sys.argv[i + 1]]
+    del sys.argv[i:i + 2]
+
+
 def phases(log):
     """[(ms, text)] of the `[x ms]` lines."""
     out = []
@@ -26,15 +33,17 @@ def phases(log):
 
 
 def breakdown(ph):
-    t = {k: 0.0 for k in ("parse", "wait for CUDA context", "sample", "upload", "exact count + top-N", "approximate count", "export", "release")}
+    t = {k: 0.0 for k in ("parse", "wait for CUDA context", "device ingest", "sample", "upload", "exact count + top-N", "approximate count", "export", "release")}
     def at(i):
         return ph[i][0]
     for i, (ms, text) in enumerate(ph[:-1]):
         dt = at(i + 1) - ms
         if text.startswith("Parsing FASTA"):
             t["parse"] += dt
-        elif text.startswith("File parsed"):
+        elif text.startswith("File parsed") or text.startswith("File mapped"):
             t["wait for CUDA context"] += dt
+        elif text.startswith("CUDA context ready") and "copying the input" in text:
+            t["device ingest"] += dt
         elif text.startswith("Sampling"):
             t["sample"] += dt
         elif text.startswith("Sampled"):
@@ -60,7 +69,7 @@ for name in (sys.argv[1:] or ["C1", "C2", "C3", "C4"]):
     for rep in range(2):
         t0 = time.perf_counter()
         p = subprocess.run([BIN, "-k", str(w["k"]), "-sn", str(w["n"]), "-sl", str(w["sl"]), "-lim", str(w["lim"]), "-v", "2",
-                            "-e", f"/tmp/apc_cli/{name}_exact", "-o", f"/tmp/apc_cli/{name}_out", path],
+                            "-e", f"/tmp/apc_cli/{name}_exact", "-o", f"/tmp/apc_cli/{name}_out", *EXTRA, path],
                            capture_output=True, text=True)
         wall = time.perf_counter() - t0
         assert p.returncode == 0, p.stderr
@@ -78,5 +87,6 @@ print()
 for name, mb, wall, main_s, t, ctx in rows:
     rest = sum(v for k, v in t.items() if k != "wait for CUDA context") / 1e3
     print(f"* {name}: everything but the wait for the CUDA context: {rest:.3f} s; {ctx}")
+print(f"\n(extra arguments: {' '.join(EXTRA) or 'none'})")
 print("\n(seconds; both ends summed; second of two runs; `main() s` = last timestamp of the -v 2 log, the rest of the process"
       " wall clock is program start and exit.)")

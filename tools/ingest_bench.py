@@ -30,8 +30,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("configs", nargs="*", default=["C2"])
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--staging", type=int, default=1, help="apc_set_option ingest_staging")
     a = ap.parse_args()
     c = ApproxCounter(0)
+    c.set_option("ingest_staging", a.staging)
     for name in a.configs:
         n, sl, seed, fastq = CONFIGS[name]
         path = os.path.join(tempfile.gettempdir(), f"ingest_{name}.{'fq' if fastq else 'fa'}")
@@ -77,7 +79,7 @@ def main():
         os.unlink(path)
         best = {k2: round(v, 3) for k2, v in best.items()}
         print(json.dumps({"config": name, "reads": n, "sl": sl, "fastq": fastq, "file_mb": round(size / 1e6, 1),
-                          "samples_identical": bool(same), "reps": a.reps,
+                          "samples_identical": bool(same), "reps": a.reps, "staging": a.staging,
                           "index_gbs_over_file": round(size / 1e6 / max(best["dev_index_ms"], 1e-6), 1),
                           "copy_gbs": round(size / 1e6 / max(best["dev_copy_ms"], 1e-6), 2), **best}), flush=True)
     c.close()
