@@ -51,6 +51,7 @@ SYMBOLS = {
     "apc_ingest_fastx": (C.c_int, [_vp, _vp, C.c_uint64, _u64p, C.POINTER(C.c_int)]),
     "apc_ingest_lengths": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp]),
     "apc_sample_resident": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, _u64p]),
+    "apc_upload_sample_peer": (C.c_int, [_vp, _vp, C.c_uint64, C.c_uint64]),
     "apc_download_sample": (C.c_int, [_vp, _vp, C.c_uint64]),
     "apc_ingest_timing": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "apc_exact_topn": (C.c_int, [_vp, C.c_uint8, C.c_float, C.c_uint64, _vp, C.c_uint64,

@@ -138,6 +138,11 @@ class ApproxCounter:
         self._check(st)
         return n.value
 
+    def upload_sample_peer(self, src, first_read, n_reads):
+        """Rows [first_read, first_read + n_reads) of the sample resident in `src` (another ApproxCounter, normally
+        on another GPU) become this context's sample, copied GPU to GPU (apc_upload_sample_peer; asynchronous)."""
+        self._check(self._lib.apc_upload_sample_peer(self._h, src._h, int(first_read), int(n_reads)))
+
     def download_sample(self):
         """ASCII rows of the resident sample -> uint8[n_reads, read_len]."""
         n, ml, _ = self.sample_info()

@@ -453,6 +453,41 @@ int apc_sample_resident(apc_ctx *c, const uint32_t *order, uint64_t n_order, uin
     return APC_OK;
 }
 
+int apc_upload_sample_peer(apc_ctx *c, const apc_ctx *src, uint64_t first_read, uint64_t n_reads) {
+    int st = apc::bind(c);
+    if (st) return st;
+    if (!src || src == c) return apc::fail(c, APC_ERR_INVALID, "src must be another context");
+    if (!src->has_sample || !src->uniform_len || !src->stage_is_sample)
+        return apc::fail(c, APC_ERR_NO_SAMPLE, "src holds no sample with ASCII rows");
+    if (first_read > src->n_reads || n_reads > src->n_reads - first_read) return apc::fail(c, APC_ERR_INVALID, "rows outside src's sample");
+    const uint32_t read_len = src->max_len;
+    if (src->device != c->device) { // direct GPU-to-GPU copies (NVLink) where the devices are peers; staged by the driver otherwise
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, c->device, src->device) == cudaSuccess && can) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return apc::fail(c, APC_ERR_CUDA, "cudaDeviceEnablePeerAccess", e);
+            (void)cudaGetLastError();
+        }
+    }
+    APC_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    const size_t bytes = (size_t)n_reads * read_len;
+    if ((st = apc::prepare_sample(c, n_reads, read_len, bytes))) return st;
+    c->uniform_len = true;
+    c->stage_is_sample = false;
+    if ((st = apc::grow(c, c->d_stage, c->stage_cap, bytes))) return st;
+    if (bytes)
+        APC_CUDA(c, cudaMemcpyPeerAsync(c->d_stage, c->device, src->d_stage + (size_t)first_read * read_len, src->device, bytes,
+                                        c->stream));
+    APC_CUDA(c, apc::launch_build_tiles_uniform(c->d_stage, n_reads, read_len, c->chunks, c->n_tiles, c->d_tiles, c->d_lens,
+                                                c->stream));
+    APC_CUDA(c, apc::launch_build_planes(*c));
+    APC_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    c->has_sample = true;
+    c->stage_is_sample = true;
+    c->timing.upload_ms = -1.f; // resolved lazily by apc_last_timing
+    return APC_OK;
+}
+
 int apc_download_sample(apc_ctx *c, uint8_t *bases_out, uint64_t capacity) {
     int st = apc::bind(c);
     if (st) return st;

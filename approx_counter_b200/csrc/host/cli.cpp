@@ -99,8 +99,8 @@ const OptSpec OPTIONS[] = {
     {"", "device", Kind::Int, "[extension] first CUDA device to use (default 0)"},
     {"", "ingest", Kind::String,
      "[extension] device (default): the input's bytes are copied to the GPU, indexed and sampled there (single-line "
-     "FASTA / 4-line FASTQ on one GPU; anything else is handed to the host parser); host: parsed and sampled by host "
-     "threads"},
+     "FASTA / 4-line FASTQ; anything else is handed to the host parser; with --gpus N the other GPUs fetch their "
+     "shard of the sample from the first, GPU to GPU); host: parsed and sampled by host threads"},
     {"", "version-check", Kind::String, "[accepted for SeqAn compatibility, ignored]"},
 };
 
@@ -327,7 +327,7 @@ int cli_main(int argc, const char **argv) {
     Reads seqs;
     uint64_t n_seqs = 0;
     bool device_ingest = false;
-    if (ingest == "device" && n_gpus == 1) {
+    if (ingest == "device") {
         // The file is mapped and paged in beside the creation of the CUDA context, then copied to the GPU, where the
         // records are indexed and every sample is gathered (apc_ingest_fastx / apc_sample_resident).
         MappedFile file;
@@ -498,6 +498,8 @@ int cli_main(int argc, const char **argv) {
                         if (g == 0) {
                             apc_set_option(c, "scan_first_read", (int64_t)first);
                             apc_set_option(c, "scan_n_reads", (int64_t)(last - first));
+                        } else if (device_ingest) { // the shard comes from GPU 0's resident sample, GPU to GPU
+                            s = apc_upload_sample_peer(c, ctx0, first, last - first);
                         } else {
                             s = apc_upload_sample_async(c, sample.data() + first * row_len, last - first, row_len);
                         }

@@ -225,6 +225,71 @@ def cpu_leg(w, ends, queries, target_s, threads=0, algo="fm"):
             "gcups": k * cols / t / 1e9, "index_build_s": build, "search_s": search}
 
 
+def ingest_leg(w, name, device):
+    """The step before the path on this workload's input file: the host route (parallel parser,
+    sampler, upload of both ends) against the device route (apc_ingest_fastx + apc_sample_resident), wall clock of the
+    second of two passes, and a byte-for-byte comparison of the samples both leave on the GPU."""
+    import mmap
+    import tempfile
+    from approx_counter_b200 import ApproxCounter, host
+    n, sl, fastq = w["n"], w["sl"], name == "C3"
+    path = os.path.join(tempfile.gettempdir(), f"apc_bench_{os.getpid()}.{'fq' if fastq else 'fa'}")
+    host.synth_write(path, w["seed"], n, sl, fastq=fastq)
+    size = os.path.getsize(path)
+    c = ApproxCounter(device)
+    out = {}
+    try:
+        same = True
+        for _ in range(2):
+            t0 = time.perf_counter()
+            reads = host.Reads(path)
+            t1 = time.perf_counter()
+            rows = []
+            for bot in (False, True):
+                s = reads.sample(n, sl, bot, 7)
+                c.upload_sample(s)
+                rows.append(s)
+            t2 = time.perf_counter()
+            reads.close()
+            with open(path, "rb") as f:
+                mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+                buf = np.frombuffer(mm, np.uint8)
+                t3 = time.perf_counter()
+                nrec, _ = c.ingest_fastx(buf)
+                t4 = time.perf_counter()
+                tm = c.ingest_timing()
+                del buf
+                mm.close()
+            order = host.shuffle_order(nrec, 7)
+            t5 = time.perf_counter()
+            kernels_ms = 0.0
+            for bot in (False, True):
+                c.sample_resident(n, sl, bot, order)
+                kernels_ms += c.ingest_timing()["sample_ms"]
+            t6 = time.perf_counter()
+            out = {"file_mb": size / 1e6, "format": "fastq" if fastq else "fasta", "records": int(nrec),
+                   "host_ms": (t2 - t0) * 1e3, "host_parse_ms": (t1 - t0) * 1e3, "host_sample_upload_ms": (t2 - t1) * 1e3,
+                   "device_ms": (t4 - t3 + t6 - t5) * 1e3, "device_copy_ms": tm["copy_ms"], "device_index_ms": tm["index_ms"],
+                   "device_sample_ms": (t6 - t5) * 1e3, "device_sample_kernels_ms": kernels_ms,
+                   "shuffle_ms_not_counted": (t5 - t4) * 1e3,
+                   "copy_gbs": size / 1e6 / max(tm["copy_ms"], 1e-6), "index_gbs": size / 1e6 / max(tm["index_ms"], 1e-6),
+                   "what": "input file of this workload -> both ends' samples resident as scan tiles and bit planes; host: "
+                           "parallel parser + sampler + apc_upload_sample; device: apc_ingest_fastx (file bytes through "
+                           "page-locked staging, newline and record index kernels) + apc_sample_resident (pick, gather, "
+                           "layout kernels); wall clock, second of two passes, page cache warm; the shuffle of the ids "
+                           "(host, both routes) is outside both figures' difference"}
+        for bot in (False, True):  # the device route's last sample is the end sample: compare both ends once more
+            c.sample_resident(n, sl, bot, order)
+            same = same and np.array_equal(c.download_sample(), rows[int(bot)])
+        out["samples_identical"] = bool(same)
+        if not same:
+            raise SystemExit("bench.py: PARITY FAILURE — device ingest and host ingest leave different samples")
+    finally:
+        c.close()
+        os.unlink(path)
+    return out
+
+
 def reference_queries(w, ends):
     """Top-`lim` exact k-mers of each end with the CPU restatement (:874, :898; all host threads for the count,
     threshold-cut top-N — both held equal to the plain restatement in tests/test_oracle.py).  Set-up of the
@@ -713,7 +778,7 @@ def run_b200(args, w):
     }
 
     # ---- N = 1 only: CPU baseline on a bounded sample + oracle spot check, the floor, the wide-offset stream
-    cpu = floor = wide = None
+    cpu = floor = wide = ingest = None
     if world == 1 and not args.no_cpu_baseline:
         import __graft_entry__ as g
         g.build_oracle()
@@ -762,6 +827,12 @@ def run_b200(args, w):
                 "executed_over_planned": wr["stats"]["lop3_executed"] / max(wr["stats"]["lop3_planned"], 1.0),
                 "what": "same generator with the adapter offsets uniform in 0..sl/2 (default 0..7), own top-lim queries"}
         jw.close()
+        try:
+            ingest = ingest_leg(w, args.workload, local_rank)
+        except SystemExit:
+            raise
+        except Exception as e:  # noqa: BLE001 — the leg is an extra: a full /tmp must not cost the bench line
+            ingest = {"error": repr(e)}
     else:
         job.close()
 
@@ -796,6 +867,8 @@ def run_b200(args, w):
         "floor_value": floor["value"] if floor else None, "floor": floor,
         "wide_offset_value": wide["value"] if wide else None, "wide_offset": wide,
         "c2_weak_value": c2["value"] if c2 else None, "c2_weak": c2,
+        "ingest_device_ms": ingest.get("device_ms") if ingest else None,
+        "ingest_host_ms": ingest.get("host_ms") if ingest else None, "ingest": ingest,
         "cpu_baseline": cpu,
     }
     emit(line)

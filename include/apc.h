@@ -129,6 +129,16 @@ int apc_ingest_lengths(apc_ctx *ctx, uint64_t first, uint64_t n,
 int apc_sample_resident(apc_ctx *ctx, const uint32_t *order, uint64_t n_order,
                         uint64_t nb_sample, uint32_t cut, int bot,
                         uint64_t *n_sampled_out);
+/* Multi-GPU hosts: rows [first_read, first_read + n_reads) of the ASCII sample
+ * resident in `src` (another context, normally another GPU, after
+ * apc_sample_resident or apc_upload_sample there) become the sample of `ctx`,
+ * copied GPU to GPU (cudaMemcpyPeerAsync: over NVLink where the devices are
+ * peers) — a rank's shard of the reads without a trip through the host.  src's
+ * sample must be complete (apc_sample_resident and apc_upload_sample
+ * synchronise) and must not be replaced before apc_sync(ctx) returns;
+ * asynchronous like apc_upload_sample_async. */
+int apc_upload_sample_peer(apc_ctx *ctx, const apc_ctx *src, uint64_t first_read,
+                           uint64_t n_reads);
 /* ASCII rows (n_reads x read_len, see apc_sample_info) of the resident sample
  * as uploaded or gathered — what sampleSequences would have returned.  Not
  * available after apc_upload_sample_ragged. */

@@ -212,3 +212,29 @@ def test_staged_copy_of_a_large_file(built, counter, tmp_path):
                 assert np.array_equal(counter.download_sample(), want[bot])
     finally:
         counter.set_option("ingest_staging", 1)
+
+
+def test_peer_upload_of_a_shard(built, counter):
+    """apc_upload_sample_peer: rows of one context's resident sample become another context's sample (here two
+    contexts on one GPU; across GPUs the same call copies over NVLink — tests/test_gpu_multi.py runs the binary with
+    --gpus N through it)."""
+    from approx_counter_b200 import ApcError, ApproxCounter, host
+    n, sl, k = 5000, 80, 14
+    rows = host.synth_ends(4141, 0, n, sl, True)
+    data = b"".join(b">r%d\n" % i + b"ACGT" * 25 + rows[i].tobytes() + b"\n" for i in range(n))
+    assert counter.ingest_fastx(data) == (n, False)
+    assert counter.sample_resident(n, sl, True) == n
+    assert np.array_equal(counter.download_sample(), rows)
+    km, _, _, _ = counter.count_kmers_topn(k, 1e30, 120)
+    whole = counter.errorCount(km, k)
+    with ApproxCounter(0) as other:
+        total = np.zeros(len(km), np.uint64)
+        for first, cnt in ((0, 1024), (1024, 2976), (4000, 1000), (5000, 0)):
+            other.upload_sample_peer(counter, first, cnt)
+            assert np.array_equal(other.download_sample(), rows[first:first + cnt])
+            total += other.errorCount(km, k)
+        assert np.array_equal(total, whole)
+        with pytest.raises(ApcError):
+            other.upload_sample_peer(counter, 4000, 1001)
+        with pytest.raises(ApcError):
+            other.upload_sample_peer(other, 0, 1)

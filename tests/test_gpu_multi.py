@@ -71,11 +71,15 @@ def test_binary_multi_gpu_matches_single(built, tmp_path, gpus):
     path = tmp_path / "reads.fa"
     host.synth_write(path, 31, 5003, 100)
     outs = {}
-    for g in (1, gpus):
-        o = tmp_path / f"o{g}"
-        p = subprocess.run([BIN, "-k", "16", "-sn", "5003", "-sl", "100", "-lim", "200", "-e", str(tmp_path / f"e{g}"),
-                            "-o", str(o), "--gpus", str(g), str(path)], capture_output=True, text=True, timeout=300)
+    # --ingest device (the default): GPU 0 parses and samples, the others fetch their shard of the sample from it
+    # (apc_upload_sample_peer); --ingest host: every shard is uploaded from the host's copy of the sample
+    for g, ingest in ((1, "device"), (gpus, "device"), (gpus, "host")):
+        o = tmp_path / f"o{g}{ingest}"
+        p = subprocess.run([BIN, "-k", "16", "-sn", "5003", "-sl", "100", "-lim", "200", "-e", str(tmp_path / f"e{g}{ingest}"),
+                            "-o", str(o), "--gpus", str(g), "--ingest", ingest, "-v", "2", str(path)],
+                           capture_output=True, text=True, timeout=300)
         assert p.returncode == 0, p.stderr
-        outs[g] = [(tmp_path / f"{pre}{g}_0.{end}").read_bytes() for pre in ("o", "e") for end in ("start", "end")]
-    assert outs[1] == outs[gpus]
-    assert len(outs[1][0].splitlines()) == 200
+        assert ("indexed on the GPU" in p.stdout) == (ingest == "device")
+        outs[g, ingest] = [(tmp_path / f"{pre}{g}{ingest}_0.{end}").read_bytes() for pre in ("o", "e") for end in ("start", "end")]
+    assert outs[1, "device"] == outs[gpus, "device"] == outs[gpus, "host"]
+    assert len(outs[1, "device"][0].splitlines()) == 200
