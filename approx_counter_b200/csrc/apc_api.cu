@@ -414,17 +414,21 @@ int apc_sample_resident(apc_ctx *c, const uint32_t *order, uint64_t n_order, uin
     const uint32_t row_len = cut + (bot ? 1u : 0u);
     APC_CUDA(c, cudaEventRecord(c->ev_ingest[2], c->stream));
     uint64_t n_sampled = 0;
-    uint32_t *d_ord = nullptr, *d_flags = nullptr, *d_pos = nullptr, *d_chosen = nullptr;
+    uint32_t *d_ord = nullptr, *d_flags = nullptr, *d_pos = nullptr;
+    uint64_t *d_src_off = nullptr;
     if (n && cut && nb_sample) { // :461 takes nothing when cut == 0 (current_cut_size > 0 is part of the test)
-        if ((st = apc::grow(c, c->d_pick, c->pick_cap, (size_t)n * 4 * sizeof(uint32_t)))) return st;
-        d_ord = c->d_pick, d_flags = d_ord + n, d_pos = d_flags + n, d_chosen = d_pos + n;
+        const uint64_t n4 = (n + 3) & ~(uint64_t)3; // keeps the u64 part aligned
+        if ((st = apc::grow(c, c->d_pick, c->pick_cap, (size_t)n4 * 3 * sizeof(uint32_t) + (size_t)n * sizeof(uint64_t)))) return st;
+        d_ord = c->d_pick, d_flags = d_ord + n4, d_pos = d_flags + n4;
+        d_src_off = reinterpret_cast<uint64_t *>(d_pos + n4);
         size_t temp_bytes = 0;
         APC_CUDA(c, apc::ingest_prefix_u32(nullptr, temp_bytes, d_flags, d_pos, n, c->stream));
         if ((st = apc::grow(c, c->d_ingest_temp, c->ingest_temp_cap, temp_bytes))) return st;
         if (order) APC_CUDA(c, cudaMemcpyAsync(d_ord, order, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
         APC_CUDA(c, cudaMemsetAsync(c->d_ingest_flag, 0, 4 * sizeof(uint32_t), c->stream));
-        APC_CUDA(c, apc::launch_pick_reads(order ? d_ord : nullptr, n, c->d_rec_len, 2ull * cut, nb_sample, d_flags, d_pos,
-                                           d_chosen, c->d_ingest_temp, c->ingest_temp_cap, c->d_ingest_flag, c->stream));
+        APC_CUDA(c, apc::launch_pick_reads(order ? d_ord : nullptr, n, c->d_rec_start, c->d_rec_len, cut, bot != 0, nb_sample,
+                                           d_flags, d_pos, d_src_off, c->d_ingest_temp, c->ingest_temp_cap, c->d_ingest_flag,
+                                           c->stream));
         uint32_t last[2] = {0, 0}, flag = 0;
         APC_CUDA(c, cudaMemcpyAsync(&last[0], d_pos + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         APC_CUDA(c, cudaMemcpyAsync(&last[1], d_flags + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -438,8 +442,7 @@ int apc_sample_resident(apc_ctx *c, const uint32_t *order, uint64_t n_order, uin
     c->uniform_len = true;
     c->stage_is_sample = false;
     if ((st = apc::grow(c, c->d_stage, c->stage_cap, bytes))) return st;
-    APC_CUDA(c, apc::launch_gather_ends(c->d_file, c->d_rec_start, c->d_rec_len, d_chosen, n_sampled, row_len, cut, bot != 0,
-                                        c->d_stage, c->stream));
+    APC_CUDA(c, apc::launch_gather_ends(c->d_file, d_src_off, n_sampled, row_len, c->d_stage, c->stream));
     APC_CUDA(c, apc::launch_build_tiles_uniform(c->d_stage, n_sampled, row_len, c->chunks, c->n_tiles, c->d_tiles, c->d_lens,
                                                 c->stream));
     APC_CUDA(c, apc::launch_build_planes(*c));

@@ -178,7 +178,7 @@ struct Ctx {
     size_t pinned_cap = 0;
 
     // resident input file and its record index (device ingest, ingest_kernels.cu)
-    uint8_t *d_file = nullptr;       // the file's bytes, padded with zeros to a whole number of 16 KB tiles
+    uint8_t *d_file = nullptr;       // the file's bytes, padded with zeros to a whole number of tiles
     size_t file_cap = 0;
     uint64_t *d_tile_nl = nullptr;   // newlines per tile, then (in place) their exclusive prefix sum; [tiles + 1]
     size_t tile_nl_cap = 0;
@@ -188,7 +188,7 @@ struct Ctx {
     size_t rec_start_cap = 0;
     uint32_t *d_rec_len = nullptr;   // per record: bases on that line
     size_t rec_len_cap = 0;
-    uint32_t *d_pick = nullptr;      // sampling scratch: order | eligible flags | their prefix sum | chosen ids, n u32 each
+    uint32_t *d_pick = nullptr;      // sampling scratch: order | eligible flags | their prefix sum (n u32 each) | file offsets of the chosen ends (n u64)
     size_t pick_cap = 0;
     uint8_t *h_file_stage[2] = {nullptr, nullptr}; // page-locked staging of the file copy (two pieces in flight)
     cudaEvent_t ev_file_stage[2] = {};
@@ -239,7 +239,7 @@ cudaError_t launch_build_tiles_ragged(const uint8_t *d_ascii, const uint64_t *d_
                                       uint32_t *d_lens, cudaStream_t s);
 
 // ingest_kernels.cu
-constexpr uint64_t kIngestTileBytes = 16384;
+constexpr uint64_t kIngestTileBytes = 4096;  // one warp: 8 steps of 32 x 16 bytes
 constexpr uint64_t kIngestStageBytes = (uint64_t)16 << 20; // one staging piece of the file copy
 cudaError_t launch_count_newlines(const uint8_t *d_file, uint64_t n_tiles, uint64_t *d_tile_nl, cudaStream_t s);
 cudaError_t launch_write_newlines(const uint8_t *d_file, uint64_t n_tiles, const uint64_t *d_tile_base, uint64_t *d_nl,
@@ -250,11 +250,10 @@ cudaError_t ingest_prefix_u32(void *d_temp, size_t &temp_bytes, const uint32_t *
 cudaError_t launch_index_records(const uint8_t *d_file, const uint64_t *d_nl, uint64_t n_nl, uint64_t n_bytes, bool fastq,
                                  uint64_t n_records, uint64_t *d_rec_start, uint32_t *d_rec_len, uint32_t *d_flag,
                                  cudaStream_t s);
-cudaError_t launch_pick_reads(const uint32_t *d_order, uint64_t n, const uint32_t *d_rec_len, uint64_t min_len,
-                              uint64_t nb_sample, uint32_t *d_flags, uint32_t *d_pos, uint32_t *d_chosen, void *d_temp,
-                              size_t temp_bytes, uint32_t *d_flag, cudaStream_t s);
-cudaError_t launch_gather_ends(const uint8_t *d_file, const uint64_t *d_rec_start, const uint32_t *d_rec_len,
-                               const uint32_t *d_chosen, uint64_t n_sampled, uint32_t row_len, uint32_t cut, bool bot,
+cudaError_t launch_pick_reads(const uint32_t *d_order, uint64_t n, const uint64_t *d_rec_start, const uint32_t *d_rec_len,
+                              uint32_t cut, bool bot, uint64_t nb_sample, uint32_t *d_flags, uint32_t *d_pos,
+                              uint64_t *d_src_off, void *d_temp, size_t temp_bytes, uint32_t *d_flag, cudaStream_t s);
+cudaError_t launch_gather_ends(const uint8_t *d_file, const uint64_t *d_src_off, uint64_t n_sampled, uint32_t row_len,
                                uint8_t *d_stage, cudaStream_t s);
 
 // scan_kernel.cu

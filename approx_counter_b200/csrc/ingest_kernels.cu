@@ -6,8 +6,8 @@
 // and end of a run, every run of -mr) is gathered from the resident bytes straight into the staging buffer the
 // layout kernels read — no host parse, no host-side copies of the read ends, no second upload.
 //
-//   count_newlines_kernel   one pass over the bytes: newlines per 16 KB tile            (HBM-bound: reads 1 B / B)
-//   [prefix sum over the tiles: cub::DeviceScan, tiles = bytes / 16384 elements]
+//   count_newlines_kernel   one pass over the bytes: newlines per 4 KB tile (one warp)   (HBM-bound: reads 1 B / B)
+//   [prefix sum over the tiles: cub::DeviceScan, tiles = bytes / 4096 elements]
 //   write_newlines_kernel   second pass: the byte offset of every newline, ascending    (reads 1 B / B, L2-warm for
 //                                                                                         files below ~100 MB)
 //   index_records_kernel    one warp per record: grammar check (header / '+' markers, quality length, no blanks
@@ -23,9 +23,9 @@
 
 namespace apc {
 
-constexpr int kIngestThreads = 256;
-constexpr int kIngestIters = (int)(kIngestTileBytes / (kIngestThreads * 16)); // uint4 loads per thread and tile
-static_assert(kIngestIters * kIngestThreads * 16 == (int)kIngestTileBytes, "tile = threads x iterations x 16 bytes");
+constexpr int kIngestThreads = 256;                                     // 8 warps, one tile each
+constexpr int kIngestIters = (int)(kIngestTileBytes / (32 * 16));       // uint4 loads per lane and tile
+static_assert(kIngestIters * 32 * 16 == (int)kIngestTileBytes, "tile = 32 lanes x iterations x 16 bytes");
 
 // bit b of the result = byte b of the 16 is '\n'
 __device__ __forceinline__ uint32_t newline_mask16(const uint4 v) {
@@ -40,44 +40,40 @@ __device__ __forceinline__ uint32_t newline_mask16(const uint4 v) {
     return m;
 }
 
+// One warp per tile of kIngestTileBytes: no shared memory, no barriers — a warp's loads of one step are one contiguous
+// 512-byte request, and the order of the newlines inside a tile is (step, lane, byte).
 __global__ void __launch_bounds__(kIngestThreads)
 count_newlines_kernel(const uint4 *__restrict__ file, const uint64_t n_tiles, uint64_t *__restrict__ tile_nl) {
-    __shared__ uint32_t s_warp[kIngestThreads / 32];
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint4 *p = file + tile * (kIngestTileBytes / 16) + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * (kIngestThreads / 32);
+    for (uint64_t tile = (uint64_t)blockIdx.x * (kIngestThreads / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += warps) {
+        const uint4 *p = file + tile * (kIngestTileBytes / 16) + lane;
         uint4 v[kIngestIters];
 #pragma unroll
-        for (int it = 0; it < kIngestIters; it++) v[it] = __ldg(p + it * kIngestThreads);
+        for (int it = 0; it < kIngestIters; it++) v[it] = __ldg(p + it * 32);
         uint32_t c = 0;
 #pragma unroll
         for (int it = 0; it < kIngestIters; it++) c += __popc(newline_mask16(v[it]));
         c = __reduce_add_sync(0xFFFFFFFFu, c);
-        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t t = 0;
-#pragma unroll
-            for (int w = 0; w < kIngestThreads / 32; w++) t += s_warp[w];
-            tile_nl[tile] = t;
-        }
-        __syncthreads();
+        if (lane == 0) tile_nl[tile] = c;
     }
 }
 
 __global__ void __launch_bounds__(kIngestThreads)
 write_newlines_kernel(const uint4 *__restrict__ file, const uint64_t n_tiles, const uint64_t *__restrict__ tile_base,
                       uint64_t *__restrict__ nl) {
-    __shared__ uint32_t s_warp[kIngestThreads / 32];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint4 *p = file + tile * (kIngestTileBytes / 16) + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * (kIngestThreads / 32);
+    for (uint64_t tile = (uint64_t)blockIdx.x * (kIngestThreads / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += warps) {
+        const uint4 *p = file + tile * (kIngestTileBytes / 16) + lane;
         uint4 v[kIngestIters];
 #pragma unroll
-        for (int it = 0; it < kIngestIters; it++) v[it] = __ldg(p + it * kIngestThreads);
+        for (int it = 0; it < kIngestIters; it++) v[it] = __ldg(p + it * 32);
         uint64_t base = tile_base[tile];
 #pragma unroll
         for (int it = 0; it < kIngestIters; it++) {
             uint32_t m = newline_mask16(v[it]);
+            if (!__any_sync(0xFFFFFFFFu, m != 0)) continue; // most 512-byte steps of a read file hold one newline or none
             const uint32_t c = __popc(m);
             uint32_t incl = c; // inclusive prefix over the warp
 #pragma unroll
@@ -85,23 +81,13 @@ write_newlines_kernel(const uint4 *__restrict__ file, const uint64_t n_tiles, co
                 const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
                 if (lane >= (uint32_t)d) incl += o;
             }
-            if (lane == 31) s_warp[warp] = incl;
-            __syncthreads();
-            uint32_t before = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < kIngestThreads / 32; w++) {
-                const uint32_t t = s_warp[w];
-                before += (uint32_t)w < warp ? t : 0;
-                total += t;
-            }
-            uint64_t at = base + before + incl - c;
-            const uint64_t byte0 = tile * kIngestTileBytes + ((uint64_t)it * kIngestThreads + threadIdx.x) * 16;
+            uint64_t at = base + incl - c;
+            const uint64_t byte0 = tile * kIngestTileBytes + ((uint64_t)it * 32 + lane) * 16;
             while (m) {
                 nl[at++] = byte0 + (uint32_t)(__ffs((int)m) - 1);
                 m &= m - 1;
             }
-            base += total;
-            __syncthreads();
+            base += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
     }
 }
@@ -131,22 +117,45 @@ __device__ __forceinline__ uint32_t blank_mask16(const uint4 v) {
 
 constexpr int kIndexWarps = 8;
 
+// number of trailing bytes of [b, e) for which pred holds: lanes 0..7 look at the last eight bytes at once, the rare
+// longer run is walked
+template <typename Pred>
+__device__ __forceinline__ uint64_t strip_tail(const uint8_t *file, uint64_t b, uint64_t e, uint32_t lane, Pred pred) {
+    const bool mine = lane < 8 && e > b + lane;
+    const uint32_t hit = __ballot_sync(0xFFFFFFFFu, mine && pred(file[e - 1 - (mine ? lane : 0)]));
+    const uint32_t run = (uint32_t)__ffs((int)~hit) - 1; // consecutive hits from the last byte backwards
+    e -= min(run, 8u);
+    if (run >= 8)
+        while (e > b && pred(file[e - 1])) e--;
+    return e;
+}
+
 // One warp per record.  FASTA: lines 2r (header, '>') and 2r+1 (sequence).  FASTQ: lines 4r ('@' header), 4r+1
 // (sequence), 4r+2 ('+'), 4r+3 (quality, as long as the sequence).  Trailing CR / blanks of the sequence line are
 // dropped like the host parser does; blanks inside it, or any other arrangement of lines, raise the flag.
+// The record's line boundaries are fetched by the first lanes in one step and handed round with shuffles.
 template <bool FASTQ>
 __global__ void __launch_bounds__(kIndexWarps * 32)
 index_records_kernel(const LineTable t, const uint64_t n_records, uint64_t *__restrict__ rec_start,
                      uint32_t *__restrict__ rec_len, uint32_t *__restrict__ flag) {
+    constexpr int PER = FASTQ ? 4 : 2;
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t r = (uint64_t)blockIdx.x * kIndexWarps + (threadIdx.x >> 5);
     if (r >= n_records) return;
-    const uint64_t l0 = r * (FASTQ ? 4 : 2);
-    bool bad = t.file[t.begin(l0)] != (FASTQ ? '@' : '>'); // an empty header line reads its own '\n' here
-    const uint64_t sb = t.begin(l0 + 1);
-    uint64_t se = t.end(l0 + 1);
-    while (se > sb && is_blank(t.file[se - 1])) se--;
-    if (se > sb) bad |= t.file[sb] == (FASTQ ? '+' : '>');
+    const uint64_t l0 = r * PER;
+    // lane i <= PER: the end of line l0 - 1 + i (lane 0: the newline in front of the record, or "-1")
+    uint64_t edge = 0;
+    if (lane <= PER) {
+        const uint64_t line = l0 + lane; // edge = end(line - 1)
+        edge = line == 0 ? ~(uint64_t)0 : (line - 1 < t.n_nl ? t.nl[line - 1] : t.n_bytes);
+    }
+    const uint64_t hb = __shfl_sync(0xFFFFFFFFu, edge, 0) + 1;  // header line begins
+    const uint64_t sb = __shfl_sync(0xFFFFFFFFu, edge, 1) + 1;  // sequence line
+    uint64_t se = __shfl_sync(0xFFFFFFFFu, edge, 2);
+    bool bad = false;
+    if (lane == 0) bad = t.file[hb] != (FASTQ ? '@' : '>'); // an empty header line reads its own '\n' here
+    se = strip_tail(t.file, sb, se, lane, [](uint8_t ch) { return is_blank(ch); });
+    if (lane == 1 && se > sb) bad = t.file[sb] == (FASTQ ? '+' : '>');
     // blanks inside the sequence: the line is read as aligned 16-byte pieces (the file buffer is 256-byte aligned and
     // padded to whole tiles), one per lane and step, bytes outside [sb, se) masked out
     for (uint64_t at = (sb & ~(uint64_t)15) + 16 * lane; at < se; at += 16 * 32) {
@@ -157,10 +166,11 @@ index_records_kernel(const LineTable t, const uint64_t n_records, uint64_t *__re
         bad |= m != 0;
     }
     if (FASTQ) {
-        bad |= t.file[t.begin(l0 + 2)] != '+';
-        const uint64_t qb = t.begin(l0 + 3);
-        uint64_t qe = t.end(l0 + 3);
-        while (qe > qb && t.file[qe - 1] == '\r') qe--;
+        const uint64_t pb = __shfl_sync(0xFFFFFFFFu, edge, 2) + 1; // '+' line
+        const uint64_t qb = __shfl_sync(0xFFFFFFFFu, edge, 3) + 1; // quality line
+        uint64_t qe = __shfl_sync(0xFFFFFFFFu, edge, 4);
+        if (lane == 2) bad |= t.file[pb] != '+';
+        qe = strip_tail(t.file, qb, qe, lane, [](uint8_t ch) { return ch == '\r'; });
         bad |= (qe - qb) != (se - sb);
     }
     bad |= (se - sb) > 0xFFFFFFFFull;
@@ -186,35 +196,42 @@ __global__ void pick_flag_kernel(const uint32_t *__restrict__ order, const uint6
     flags[i] = rec_len[id] >= min_len ? 1u : 0u;
 }
 
+// chosen reads in sampling order, and where each one's sampled end begins in the file: prefix(seq, cut) (:466) starts
+// at the sequence, suffix(seq, len - 1 - cut) (:463: cut + 1 bases) cut + 1 bases before its end
 __global__ void pick_choose_kernel(const uint32_t *__restrict__ order, const uint64_t n, const uint32_t *__restrict__ flags,
-                                   const uint32_t *__restrict__ pos, const uint64_t nb_sample, uint32_t *__restrict__ chosen) {
+                                   const uint32_t *__restrict__ pos, const uint64_t nb_sample,
+                                   const uint64_t *__restrict__ rec_start, const uint32_t *__restrict__ rec_len,
+                                   const uint32_t cut, const bool bot, uint64_t *__restrict__ src_off) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (flags[i] && pos[i] < nb_sample) chosen[pos[i]] = order ? order[i] : (uint32_t)i;
+    if (flags[i] && pos[i] < nb_sample) {
+        const uint32_t id = order ? order[i] : (uint32_t)i;
+        src_off[pos[i]] = rec_start[id] + (bot ? (uint64_t)rec_len[id] - 1 - cut : 0);
+    }
 }
 
-// row j of the sample = prefix(seq, cut) (:466) or suffix(seq, len - 1 - cut) (:463: cut + 1 bases) of read chosen[j].
-// One thread fills 16 consecutive bytes of the row-major sample (one 128-bit store; they may straddle two rows).
-__global__ void gather_ends_kernel(const uint8_t *__restrict__ file, const uint64_t *__restrict__ rec_start,
-                                   const uint32_t *__restrict__ rec_len, const uint32_t *__restrict__ chosen,
-                                   const uint64_t n_bytes_out, const uint32_t row_len, const uint32_t cut, const bool bot,
-                                   uint8_t *__restrict__ stage) {
+// row j of the sample = row_len bytes of the file from src_off[j].  One thread fills 16 consecutive bytes of the
+// row-major sample (one 128-bit store; they may straddle two rows).
+__global__ void gather_ends_kernel(const uint8_t *__restrict__ file, const uint64_t *__restrict__ src_off,
+                                   const uint64_t n_bytes_out, const uint32_t row_len, uint8_t *__restrict__ stage) {
     const uint64_t idx = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
     if (idx >= n_bytes_out) return;
     uint64_t j = idx / row_len;
     uint32_t o = (uint32_t)(idx - j * row_len);
-    uint32_t id = chosen[j];
-    const uint8_t *src = file + rec_start[id] + (bot ? (uint64_t)rec_len[id] - 1 - cut : 0);
     const uint32_t n = (uint32_t)min((uint64_t)16, n_bytes_out - idx);
+    const uint64_t rows = n_bytes_out / row_len;
+    const uint8_t *src = file + src_off[j];
+    uint64_t next_off = j + 1 < rows ? src_off[j + 1] : 0; // requested together with this row's
     uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
     for (uint32_t b = 0; b < 16; b++) {
         if (b < n) {
             w[b >> 2] |= (uint32_t)src[o] << (8 * (b & 3));
-            if (++o == row_len && b + 1 < n) { // next row
+            if (++o == row_len) { // on to the next row (rows shorter than 16 bytes: more than once)
                 o = 0;
-                id = chosen[++j];
-                src = file + rec_start[id] + (bot ? (uint64_t)rec_len[id] - 1 - cut : 0);
+                j++;
+                src = file + next_off;
+                if (row_len < 16 && j + 1 < rows) next_off = src_off[j + 1];
             }
         }
     }
@@ -233,7 +250,7 @@ static unsigned grid_for(uint64_t items, int per_block) {
 
 cudaError_t launch_count_newlines(const uint8_t *d_file, uint64_t n_tiles, uint64_t *d_tile_nl, cudaStream_t s) {
     if (!n_tiles) return cudaSuccess;
-    count_newlines_kernel<<<grid_for(n_tiles, 1), kIngestThreads, 0, s>>>(reinterpret_cast<const uint4 *>(d_file), n_tiles,
+    count_newlines_kernel<<<grid_for(n_tiles, kIngestThreads / 32), kIngestThreads, 0, s>>>(reinterpret_cast<const uint4 *>(d_file), n_tiles,
                                                                          d_tile_nl);
     return cudaGetLastError();
 }
@@ -241,7 +258,7 @@ cudaError_t launch_count_newlines(const uint8_t *d_file, uint64_t n_tiles, uint6
 cudaError_t launch_write_newlines(const uint8_t *d_file, uint64_t n_tiles, const uint64_t *d_tile_base, uint64_t *d_nl,
                                   cudaStream_t s) {
     if (!n_tiles) return cudaSuccess;
-    write_newlines_kernel<<<grid_for(n_tiles, 1), kIngestThreads, 0, s>>>(reinterpret_cast<const uint4 *>(d_file), n_tiles,
+    write_newlines_kernel<<<grid_for(n_tiles, kIngestThreads / 32), kIngestThreads, 0, s>>>(reinterpret_cast<const uint4 *>(d_file), n_tiles,
                                                                          d_tile_base, d_nl);
     return cudaGetLastError();
 }
@@ -267,25 +284,24 @@ cudaError_t launch_index_records(const uint8_t *d_file, const uint64_t *d_nl, ui
     return cudaGetLastError();
 }
 
-cudaError_t launch_pick_reads(const uint32_t *d_order, uint64_t n, const uint32_t *d_rec_len, uint64_t min_len,
-                              uint64_t nb_sample, uint32_t *d_flags, uint32_t *d_pos, uint32_t *d_chosen, void *d_temp,
-                              size_t temp_bytes, uint32_t *d_flag, cudaStream_t s) {
+cudaError_t launch_pick_reads(const uint32_t *d_order, uint64_t n, const uint64_t *d_rec_start, const uint32_t *d_rec_len,
+                              uint32_t cut, bool bot, uint64_t nb_sample, uint32_t *d_flags, uint32_t *d_pos,
+                              uint64_t *d_src_off, void *d_temp, size_t temp_bytes, uint32_t *d_flag, cudaStream_t s) {
     if (!n) return cudaSuccess;
-    pick_flag_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_order, n, d_rec_len, min_len, d_flags, d_flag);
+    pick_flag_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_order, n, d_rec_len, 2ull * cut, d_flags, d_flag);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if ((e = ingest_prefix_u32(d_temp, temp_bytes, d_flags, d_pos, n, s)) != cudaSuccess) return e;
-    pick_choose_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_order, n, d_flags, d_pos, nb_sample, d_chosen);
+    pick_choose_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_order, n, d_flags, d_pos, nb_sample, d_rec_start, d_rec_len, cut, bot,
+                                                      d_src_off);
     return cudaGetLastError();
 }
 
-cudaError_t launch_gather_ends(const uint8_t *d_file, const uint64_t *d_rec_start, const uint32_t *d_rec_len,
-                               const uint32_t *d_chosen, uint64_t n_sampled, uint32_t row_len, uint32_t cut, bool bot,
+cudaError_t launch_gather_ends(const uint8_t *d_file, const uint64_t *d_src_off, uint64_t n_sampled, uint32_t row_len,
                                uint8_t *d_stage, cudaStream_t s) {
     const uint64_t n_out = n_sampled * row_len;
     if (!n_out) return cudaSuccess;
-    gather_ends_kernel<<<grid_for((n_out + 15) / 16, 256), 256, 0, s>>>(d_file, d_rec_start, d_rec_len, d_chosen, n_out, row_len, cut,
-                                                          bot, d_stage);
+    gather_ends_kernel<<<grid_for((n_out + 15) / 16, 256), 256, 0, s>>>(d_file, d_src_off, n_out, row_len, d_stage);
     return cudaGetLastError();
 }
 
