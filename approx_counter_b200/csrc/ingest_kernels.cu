@@ -117,69 +117,68 @@ __device__ __forceinline__ uint32_t blank_mask16(const uint4 v) {
 
 constexpr int kIndexWarps = 8;
 
-// number of trailing bytes of [b, e) for which pred holds: lanes 0..7 look at the last eight bytes at once, the rare
-// longer run is walked
-template <typename Pred>
-__device__ __forceinline__ uint64_t strip_tail(const uint8_t *file, uint64_t b, uint64_t e, uint32_t lane, Pred pred) {
-    const bool mine = lane < 8 && e > b + lane;
-    const uint32_t hit = __ballot_sync(0xFFFFFFFFu, mine && pred(file[e - 1 - (mine ? lane : 0)]));
-    const uint32_t run = (uint32_t)__ffs((int)~hit) - 1; // consecutive hits from the last byte backwards
-    e -= min(run, 8u);
-    if (run >= 8)
-        while (e > b && pred(file[e - 1])) e--;
-    return e;
+// blanks among the 16 bytes at `at` (16-byte aligned) that lie inside [sb, se); 0 when the piece is outside
+__device__ __forceinline__ uint32_t blanks_inside(const uint8_t *file, uint64_t at, uint64_t sb, uint64_t se) {
+    if (at >= se) return 0;
+    uint32_t m = blank_mask16(__ldg(reinterpret_cast<const uint4 *>(file + at)));
+    if (at < sb) m &= 0xFFFFu << (uint32_t)(sb - at);
+    if (at + 16 > se) m &= 0xFFFFu >> (uint32_t)(at + 16 - se);
+    return m;
 }
 
-// One warp per record.  FASTA: lines 2r (header, '>') and 2r+1 (sequence).  FASTQ: lines 4r ('@' header), 4r+1
-// (sequence), 4r+2 ('+'), 4r+3 (quality, as long as the sequence).  Trailing CR / blanks of the sequence line are
-// dropped like the host parser does; blanks inside it, or any other arrangement of lines, raise the flag.
-// The record's line boundaries are fetched by the first lanes in one step and handed round with shuffles.
+// One warp per 32 consecutive records.  FASTA: lines 2r (header, '>') and 2r+1 (sequence).  FASTQ: lines 4r ('@'
+// header), 4r+1 (sequence), 4r+2 ('+'), 4r+3 (quality, as long as the sequence).  Trailing CR / blanks of the sequence
+// line are dropped like the host parser does; blanks inside it, or any other arrangement of lines, raise the flag.
+// First every lane settles the line boundaries and marker bytes of its own record (the loads of 32 records in flight
+// together), then the warp reads the 32 sequence lines one after the other as aligned 16-byte pieces per lane, two
+// 512-byte steps requested at a time.
 template <bool FASTQ>
 __global__ void __launch_bounds__(kIndexWarps * 32)
 index_records_kernel(const LineTable t, const uint64_t n_records, uint64_t *__restrict__ rec_start,
                      uint32_t *__restrict__ rec_len, uint32_t *__restrict__ flag) {
     constexpr int PER = FASTQ ? 4 : 2;
     const uint32_t lane = threadIdx.x & 31;
-    const uint64_t r = (uint64_t)blockIdx.x * kIndexWarps + (threadIdx.x >> 5);
-    if (r >= n_records) return;
-    const uint64_t l0 = r * PER;
-    // lane i <= PER: the end of line l0 - 1 + i (lane 0: the newline in front of the record, or "-1")
-    uint64_t edge = 0;
-    if (lane <= PER) {
-        const uint64_t line = l0 + lane; // edge = end(line - 1)
-        edge = line == 0 ? ~(uint64_t)0 : (line - 1 < t.n_nl ? t.nl[line - 1] : t.n_bytes);
+    const uint64_t base = ((uint64_t)blockIdx.x * kIndexWarps + (threadIdx.x >> 5)) * 32;
+    if (base >= n_records) return;
+    const uint64_t r = base + lane;
+    const bool valid = r < n_records;
+    uint64_t edge[PER + 1]; // edge[j] = end of line PER * r - 1 + j ("-1": the newline in front of the record)
+#pragma unroll
+    for (int j = 0; j <= PER; j++) {
+        const uint64_t line = PER * r + j;
+        edge[j] = !valid ? 0 : line == 0 ? ~(uint64_t)0 : (line - 1 < t.n_nl ? t.nl[line - 1] : t.n_bytes);
     }
-    const uint64_t hb = __shfl_sync(0xFFFFFFFFu, edge, 0) + 1;  // header line begins
-    const uint64_t sb = __shfl_sync(0xFFFFFFFFu, edge, 1) + 1;  // sequence line
-    uint64_t se = __shfl_sync(0xFFFFFFFFu, edge, 2);
+    uint64_t sb = edge[1] + 1, se = edge[2];
     bool bad = false;
-    if (lane == 0) bad = t.file[hb] != (FASTQ ? '@' : '>'); // an empty header line reads its own '\n' here
-    se = strip_tail(t.file, sb, se, lane, [](uint8_t ch) { return is_blank(ch); });
-    if (lane == 1 && se > sb) bad = t.file[sb] == (FASTQ ? '+' : '>');
-    // blanks inside the sequence: the line is read as aligned 16-byte pieces (the file buffer is 256-byte aligned and
-    // padded to whole tiles), one per lane and step, bytes outside [sb, se) masked out
-    for (uint64_t at = (sb & ~(uint64_t)15) + 16 * lane; at < se; at += 16 * 32) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(t.file + at));
-        uint32_t m = blank_mask16(v);
-        if (at < sb) m &= 0xFFFFu << (uint32_t)(sb - at);
-        if (at + 16 > se) m &= 0xFFFFu >> (uint32_t)(at + 16 - se);
-        bad |= m != 0;
-    }
-    if (FASTQ) {
-        const uint64_t pb = __shfl_sync(0xFFFFFFFFu, edge, 2) + 1; // '+' line
-        const uint64_t qb = __shfl_sync(0xFFFFFFFFu, edge, 3) + 1; // quality line
-        uint64_t qe = __shfl_sync(0xFFFFFFFFu, edge, 4);
-        if (lane == 2) bad |= t.file[pb] != '+';
-        qe = strip_tail(t.file, qb, qe, lane, [](uint8_t ch) { return ch == '\r'; });
-        bad |= (qe - qb) != (se - sb);
-    }
-    bad |= (se - sb) > 0xFFFFFFFFull;
-    bad = __any_sync(0xFFFFFFFFu, bad);
-    if (lane == 0) {
+    if (valid) {
+        const uint8_t head = t.file[edge[0] + 1]; // an empty header line reads its own '\n' here
+        uint8_t plus = '+';
+        uint64_t qb = 0, qe = 0;
+        if (FASTQ) {
+            plus = t.file[edge[2] + 1];
+            qb = edge[PER - 1] + 1, qe = edge[PER];
+            while (qe > qb && t.file[qe - 1] == '\r') qe--;
+        }
+        while (se > sb && is_blank(t.file[se - 1])) se--;
+        bad = head != (FASTQ ? '@' : '>') || plus != '+' || (se - sb) > 0xFFFFFFFFull;
+        if (se > sb) bad |= t.file[sb] == (FASTQ ? '+' : '>');
+        if (FASTQ) bad |= (qe - qb) != (se - sb);
         rec_start[r] = sb;
         rec_len[r] = (uint32_t)(se - sb);
-        if (bad) atomicOr(flag, 1u);
+    } else {
+        sb = se = 0;
     }
+    // blanks inside the sequences (the file buffer is 256-byte aligned and padded to whole tiles)
+    const uint32_t count = (uint32_t)min((uint64_t)32, n_records - base);
+    for (uint32_t i = 0; i < count; i++) {
+        const uint64_t b = __shfl_sync(0xFFFFFFFFu, sb, i), e = __shfl_sync(0xFFFFFFFFu, se, i);
+        for (uint64_t at = (b & ~(uint64_t)15) + 16 * lane; at < e; at += 2 * 16 * 32) {
+            const uint32_t m0 = blanks_inside(t.file, at, b, e), m1 = blanks_inside(t.file, at + 16 * 32, b, e);
+            bad |= (m0 | m1) != 0;
+        }
+    }
+    bad = __any_sync(0xFFFFFFFFu, bad);
+    if (lane == 0 && bad) atomicOr(flag, 1u);
 }
 
 // :447-461 — position i of the (shuffled) order is taken when its read has at least 2 * cut bases
@@ -278,7 +277,7 @@ cudaError_t launch_index_records(const uint8_t *d_file, const uint64_t *d_nl, ui
                                  cudaStream_t s) {
     if (!n_records) return cudaSuccess;
     const LineTable t{d_file, d_nl, n_nl, n_bytes};
-    const unsigned grid = grid_for(n_records, kIndexWarps);
+    const unsigned grid = grid_for(n_records, kIndexWarps * 32);
     if (fastq) index_records_kernel<true><<<grid, kIndexWarps * 32, 0, s>>>(t, n_records, d_rec_start, d_rec_len, d_flag);
     else index_records_kernel<false><<<grid, kIndexWarps * 32, 0, s>>>(t, n_records, d_rec_start, d_rec_len, d_flag);
     return cudaGetLastError();
