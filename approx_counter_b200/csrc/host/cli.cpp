@@ -202,6 +202,8 @@ int gpu_fail(const char *what, apc_ctx *ctx, int st) {
 
 } // namespace
 
+bool one_shot_process = false; // set by main.cpp
+
 int cli_main(int argc, const char **argv) {
     Parsed parser;
     const ParseResult res = parse_args(argc, argv, parser);
@@ -544,6 +546,14 @@ int cli_main(int argc, const char **argv) {
             }
         }
         tab_level--;
+    }
+    if (one_shot_process) {
+        // the binary ends the process right after this call (main.cpp): the driver reclaims the device memory with the
+        // context, freeing buffer by buffer first only adds to the wall clock (0.01-1.1 s measured on C3)
+        for (Gpu &g : gpus) {
+            apc_sync(g.ctx);
+            g.ctx = nullptr;
+        }
     }
     if (v > 1) print("Releasing the GPU", tab_level);
     gpus.clear();

@@ -70,5 +70,6 @@ void synth_ends(uint64_t seed, uint64_t first, uint64_t n, uint32_t sl, bool bot
 bool synth_write(const std::string &path, uint64_t seed, uint64_t n, uint32_t sl, bool fastq);
 
 int cli_main(int argc, const char **argv);
+extern bool one_shot_process; // true: cli_main leaves the GPU contexts to the end of the process (the binary's main)
 
 } // namespace apch

@@ -6,6 +6,7 @@
 #include "host_util.h"
 
 int main(int argc, const char **argv) {
+    apch::one_shot_process = true;
     const int rc = apch::cli_main(argc, argv);
     // every output file is closed by now; skip the CUDA runtime's exit handlers (about
     // 0.7 s of context teardown that the driver does anyway when the process ends)
