@@ -85,6 +85,62 @@ static int prepare_sample(Ctx *c, uint64_t n_reads, uint32_t max_len, uint64_t t
     return APC_OK; // has_sample is set by the caller once the layout kernels are enqueued
 }
 
+// Newline index and record index of the n_eff bytes resident in d_file (tail padded with zeros up to a whole tile).
+// ok = false: the lines do not form one-sequence-line records (n_nl is valid either way, d_nl holds the newlines).
+static int ingest_index(Ctx *c, uint64_t n_eff, bool fastq, uint64_t &n_nl, uint64_t &n_rec, bool &ok) {
+    int st;
+    ok = false;
+    n_rec = 0;
+    const uint64_t n_tiles = (n_eff + kIngestTileBytes - 1) / kIngestTileBytes;
+    if ((st = grow(c, c->d_tile_nl, c->tile_nl_cap, (size_t)(n_tiles + 1) * sizeof(uint64_t)))) return st;
+    size_t temp_bytes = 0;
+    APC_CUDA(c, ingest_prefix_u64(nullptr, temp_bytes, c->d_tile_nl, n_tiles + 1, c->stream));
+    if ((st = grow(c, c->d_ingest_temp, c->ingest_temp_cap, temp_bytes))) return st;
+    APC_CUDA(c, cudaMemsetAsync(c->d_tile_nl + n_tiles, 0, sizeof(uint64_t), c->stream));
+    APC_CUDA(c, cudaMemsetAsync(c->d_ingest_flag, 0, 4 * sizeof(uint32_t), c->stream));
+    APC_CUDA(c, launch_count_newlines(c->d_file, n_tiles, c->d_tile_nl, c->stream));
+    temp_bytes = c->ingest_temp_cap;
+    APC_CUDA(c, ingest_prefix_u64(c->d_ingest_temp, temp_bytes, c->d_tile_nl, n_tiles + 1, c->stream));
+    APC_CUDA(c, cudaMemcpyAsync(&n_nl, c->d_tile_nl + n_tiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    if ((st = grow(c, c->d_nl, c->nl_cap, (size_t)std::max<uint64_t>(1, n_nl) * sizeof(uint64_t)))) return st;
+    APC_CUDA(c, launch_write_newlines(c->d_file, n_tiles, c->d_tile_nl, c->d_nl, c->stream));
+    const uint64_t n_lines = n_nl + 1, per = fastq ? 4 : 2;
+    if (n_lines % per) return APC_OK; // not 4-line FASTQ / not single-line FASTA
+    n_rec = n_lines / per;
+    if ((st = grow(c, c->d_rec_start, c->rec_start_cap, (size_t)n_rec * sizeof(uint64_t)))) return st;
+    if ((st = grow(c, c->d_rec_len, c->rec_len_cap, (size_t)n_rec * sizeof(uint32_t)))) return st;
+    APC_CUDA(c, launch_index_records(c->d_file, c->d_nl, n_nl, n_eff, fastq, n_rec, c->d_rec_start, c->d_rec_len,
+                                     c->d_ingest_flag, c->stream));
+    uint32_t flag = 0;
+    APC_CUDA(c, cudaMemcpyAsync(&flag, c->d_ingest_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    ok = flag == 0;
+    return APC_OK;
+}
+
+// FASTA with any line structure -> single-line records in a second buffer (d_nl must hold the newlines of d_file).
+static int ingest_unwrap(Ctx *c, uint64_t n_eff, uint64_t n_nl, uint64_t &n_eff2) {
+    int st;
+    const uint64_t n_lines = n_nl + 1;
+    if ((st = grow(c, c->d_line_off, c->line_off_cap, (size_t)(n_lines + 1) * sizeof(uint64_t)))) return st;
+    size_t temp_bytes = 0;
+    APC_CUDA(c, ingest_prefix_u64(nullptr, temp_bytes, c->d_line_off, n_lines + 1, c->stream));
+    if ((st = grow(c, c->d_ingest_temp, c->ingest_temp_cap, temp_bytes))) return st;
+    APC_CUDA(c, launch_measure_lines(c->d_file, c->d_nl, n_nl, n_eff, c->d_line_off, c->stream));
+    temp_bytes = c->ingest_temp_cap;
+    APC_CUDA(c, ingest_prefix_u64(c->d_ingest_temp, temp_bytes, c->d_line_off, n_lines + 1, c->stream));
+    APC_CUDA(c, cudaMemcpyAsync(&n_eff2, c->d_line_off + n_lines, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    APC_CUDA(c, cudaStreamSynchronize(c->stream));
+    const uint64_t padded = (n_eff2 + kIngestTileBytes - 1) / kIngestTileBytes * kIngestTileBytes;
+    if ((st = grow(c, c->d_file2, c->file2_cap, (size_t)std::max<uint64_t>(padded, kIngestTileBytes)))) return st;
+    APC_CUDA(c, launch_unwrap_lines(c->d_file, c->d_nl, n_nl, n_eff, c->d_line_off, c->d_file2, c->stream));
+    if (padded > n_eff2) APC_CUDA(c, cudaMemsetAsync(c->d_file2 + n_eff2, 0, padded - n_eff2, c->stream));
+    std::swap(c->d_file, c->d_file2);
+    std::swap(c->file_cap, c->file2_cap);
+    return APC_OK;
+}
+
 } // namespace apc
 
 using apc::Ctx;
@@ -172,6 +228,8 @@ void apc_destroy(apc_ctx *c) {
     cudaFree(c->d_stage_offs);
     apc::free_exact_scratch(c);
     cudaFree(c->d_file);
+    cudaFree(c->d_file2);
+    cudaFree(c->d_line_off);
     cudaFree(c->d_tile_nl);
     cudaFree(c->d_nl);
     cudaFree(c->d_rec_start);
@@ -306,7 +364,13 @@ int apc_ingest_fastx(apc_ctx *c, const uint8_t *file_bytes, uint64_t n_bytes, ui
         if (ch != '\n' && ch != '\r' && ch != ' ' && ch != '\t') break;
         n_eff--;
     }
+    // so are blank lines in front of the first record (the host parser skips them too)
+    while (n_eff > 0 && (*file_bytes == '\n' || *file_bytes == '\r' || *file_bytes == ' ' || *file_bytes == '\t')) {
+        file_bytes++;
+        n_eff--;
+    }
     c->file_bytes = n_eff;
+    c->file_unwrapped = false;
     c->ingest_ms[0] = c->ingest_ms[1] = 0.f;
     if (n_eff == 0) { // no record at all
         c->has_file = true;
@@ -319,10 +383,6 @@ int apc_ingest_fastx(apc_ctx *c, const uint8_t *file_bytes, uint64_t n_bytes, ui
     const uint64_t n_tiles = (n_eff + apc::kIngestTileBytes - 1) / apc::kIngestTileBytes;
     const uint64_t padded = n_tiles * apc::kIngestTileBytes;
     if ((st = apc::grow(c, c->d_file, c->file_cap, (size_t)padded))) return st;
-    if ((st = apc::grow(c, c->d_tile_nl, c->tile_nl_cap, (size_t)(n_tiles + 1) * sizeof(uint64_t)))) return st;
-    size_t temp_bytes = 0;
-    APC_CUDA(c, apc::ingest_prefix_u64(nullptr, temp_bytes, c->d_tile_nl, n_tiles + 1, c->stream));
-    if ((st = apc::grow(c, c->d_ingest_temp, c->ingest_temp_cap, temp_bytes))) return st;
     APC_CUDA(c, cudaEventRecord(c->ev_ingest[0], c->stream));
     if (c->opt_ingest_staging && n_eff >= 4 * apc::kIngestStageBytes) {
         // two page-locked pieces in flight: the host threads fill one (apch::parallel_copy) while the copy engine
@@ -355,35 +415,27 @@ int apc_ingest_fastx(apc_ctx *c, const uint8_t *file_bytes, uint64_t n_bytes, ui
     }
     if (padded > n_eff) APC_CUDA(c, cudaMemsetAsync(c->d_file + n_eff, 0, padded - n_eff, c->stream));
     APC_CUDA(c, cudaEventRecord(c->ev_ingest[1], c->stream));
-    APC_CUDA(c, cudaMemsetAsync(c->d_tile_nl + n_tiles, 0, sizeof(uint64_t), c->stream));
-    APC_CUDA(c, cudaMemsetAsync(c->d_ingest_flag, 0, 4 * sizeof(uint32_t), c->stream));
-    APC_CUDA(c, apc::launch_count_newlines(c->d_file, n_tiles, c->d_tile_nl, c->stream));
-    temp_bytes = c->ingest_temp_cap;
-    APC_CUDA(c, apc::ingest_prefix_u64(c->d_ingest_temp, temp_bytes, c->d_tile_nl, n_tiles + 1, c->stream));
-    uint64_t n_nl = 0;
-    APC_CUDA(c, cudaMemcpyAsync(&n_nl, c->d_tile_nl + n_tiles, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    APC_CUDA(c, cudaStreamSynchronize(c->stream));
-    const uint64_t n_lines = n_nl + 1, per = fastq ? 4 : 2;
-    if (n_lines % per)
-        return apc::fail(c, APC_ERR_FORMAT, fastq ? "line count is not a multiple of 4 (not 4-line FASTQ)"
-                                                 : "line count is odd (not single-line FASTA)");
-    const uint64_t n_rec = n_lines / per;
-    if (n_rec > 0x7FFFFFFFull) return apc::fail(c, APC_ERR_INVALID, "too many records (the reference's read ids are int)");
-    if ((st = apc::grow(c, c->d_nl, c->nl_cap, (size_t)std::max<uint64_t>(1, n_nl) * sizeof(uint64_t)))) return st;
-    if ((st = apc::grow(c, c->d_rec_start, c->rec_start_cap, (size_t)n_rec * sizeof(uint64_t)))) return st;
-    if ((st = apc::grow(c, c->d_rec_len, c->rec_len_cap, (size_t)n_rec * sizeof(uint32_t)))) return st;
-    APC_CUDA(c, apc::launch_write_newlines(c->d_file, n_tiles, c->d_tile_nl, c->d_nl, c->stream));
-    APC_CUDA(c, apc::launch_index_records(c->d_file, c->d_nl, n_nl, n_eff, fastq, n_rec, c->d_rec_start, c->d_rec_len,
-                                          c->d_ingest_flag, c->stream));
+    uint64_t n_nl = 0, n_rec = 0;
+    bool ok = false;
+    if ((st = apc::ingest_index(c, n_eff, fastq, n_nl, n_rec, ok))) return st;
+    if (!ok && !fastq) {
+        // not one sequence line per record: wrapped FASTA (or blank lines, or a header without a sequence line).  The
+        // records are re-laid as ">\n<sequence on one line>\n" in a second buffer, which then takes the file's place.
+        uint64_t n_eff2 = 0;
+        if ((st = apc::ingest_unwrap(c, n_eff, n_nl, n_eff2))) return st;
+        n_eff = n_eff2;
+        c->file_bytes = n_eff;
+        if ((st = apc::ingest_index(c, n_eff, false, n_nl, n_rec, ok))) return st;
+        c->file_unwrapped = true;
+    }
     APC_CUDA(c, cudaEventRecord(c->ev_ingest[2], c->stream));
-    uint32_t flag = 0;
-    APC_CUDA(c, cudaMemcpyAsync(&flag, c->d_ingest_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     APC_CUDA(c, cudaStreamSynchronize(c->stream));
     c->ingest_ms[0] = apc::elapsed(c->ev_ingest[0], c->ev_ingest[1]);
     c->ingest_ms[1] = apc::elapsed(c->ev_ingest[1], c->ev_ingest[2]);
-    if (flag)
+    if (!ok)
         return apc::fail(c, APC_ERR_FORMAT, fastq ? "not 4-line FASTQ (wrapped record, blank line, or quality length)"
-                                                 : "not single-line FASTA (wrapped record, blank line, or blanks in a sequence)");
+                                                 : "not FASTA the device parser takes (blanks inside a sequence line)");
+    if (n_rec > 0x7FFFFFFFull) return apc::fail(c, APC_ERR_INVALID, "too many records (the reference's read ids are int)");
     c->has_file = true;
     c->file_fastq = fastq ? 1 : 0;
     c->n_records = n_rec;

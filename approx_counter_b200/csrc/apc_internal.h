@@ -180,6 +180,11 @@ struct Ctx {
     // resident input file and its record index (device ingest, ingest_kernels.cu)
     uint8_t *d_file = nullptr;       // the file's bytes, padded with zeros to a whole number of tiles
     size_t file_cap = 0;
+    uint8_t *d_file2 = nullptr;      // wrapped FASTA re-laid as single-line records is built here, then swapped with d_file
+    size_t file2_cap = 0;
+    uint64_t *d_line_off = nullptr;  // per line of a wrapped file: bytes it contributes to the re-laid file, then their prefix sum
+    size_t line_off_cap = 0;
+    bool file_unwrapped = false;     // the resident bytes are the re-laid form, not the caller's
     uint64_t *d_tile_nl = nullptr;   // newlines per tile, then (in place) their exclusive prefix sum; [tiles + 1]
     size_t tile_nl_cap = 0;
     uint64_t *d_nl = nullptr;        // byte offsets of the newlines, ascending
@@ -250,6 +255,10 @@ cudaError_t ingest_prefix_u32(void *d_temp, size_t &temp_bytes, const uint32_t *
 cudaError_t launch_index_records(const uint8_t *d_file, const uint64_t *d_nl, uint64_t n_nl, uint64_t n_bytes, bool fastq,
                                  uint64_t n_records, uint64_t *d_rec_start, uint32_t *d_rec_len, uint32_t *d_flag,
                                  cudaStream_t s);
+cudaError_t launch_measure_lines(const uint8_t *d_file, const uint64_t *d_nl, uint64_t n_nl, uint64_t n_bytes,
+                                 uint64_t *d_line_len, cudaStream_t s);
+cudaError_t launch_unwrap_lines(const uint8_t *d_file, const uint64_t *d_nl, uint64_t n_nl, uint64_t n_bytes,
+                                const uint64_t *d_line_off, uint8_t *d_out, cudaStream_t s);
 cudaError_t launch_pick_reads(const uint32_t *d_order, uint64_t n, const uint64_t *d_rec_start, const uint32_t *d_rec_len,
                               uint32_t cut, bool bot, uint64_t nb_sample, uint32_t *d_flags, uint32_t *d_pos,
                               uint64_t *d_src_off, void *d_temp, size_t temp_bytes, uint32_t *d_flag, cudaStream_t s);

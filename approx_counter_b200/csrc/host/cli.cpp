@@ -98,9 +98,9 @@ const OptSpec OPTIONS[] = {
     {"", "gpus", Kind::Int, "[extension] number of GPUs to shard the sampled reads over (default 1)"},
     {"", "device", Kind::Int, "[extension] first CUDA device to use (default 0)"},
     {"", "ingest", Kind::String,
-     "[extension] device (default): the input's bytes are copied to the GPU, indexed and sampled there (single-line "
-     "FASTA / 4-line FASTQ; anything else is handed to the host parser; with --gpus N the other GPUs fetch their "
-     "shard of the sample from the first, GPU to GPU); host: parsed and sampled by host threads"},
+     "[extension] device (default): the input's bytes are copied to the GPU, indexed and sampled there (FASTA, 4-line "
+     "FASTQ; wrapped FASTQ and blanks inside sequence lines are handed to the host parser; with --gpus N the other GPUs "
+     "fetch their shard of the sample from the first, GPU to GPU); host: parsed and sampled by host threads"},
     {"", "version-check", Kind::String, "[accepted for SeqAn compatibility, ignored]"},
 };
 

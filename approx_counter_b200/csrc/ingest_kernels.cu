@@ -1,7 +1,6 @@
 // ingest_kernels.cu — K6: FASTA / FASTQ ingest and read sampling on the device.
 //
-// Replaces, for inputs whose records keep their sequence on ONE line (single-line FASTA, 4-line FASTQ — what
-// basecallers write), the reference's readRecords (:819-825) and the walk and copies of sampleSequences
+// Replaces, for FASTA and 4-line FASTQ (what basecallers write), the reference's readRecords (:819-825) and the walk and copies of sampleSequences
 // (:447-471): the file's bytes are copied to HBM once, the records are indexed there, and every sample (start
 // and end of a run, every run of -mr) is gathered from the resident bytes straight into the staging buffer the
 // layout kernels read — no host parse, no host-side copies of the read ends, no second upload.
@@ -15,8 +14,10 @@
 //   pick_*_kernel + prefix  the first nb_sample ids of the caller's shuffled order with length >= 2*cut (:447-461)
 //   gather_ends_kernel      prefix(cut) (:466) or the last cut+1 bases (:463) of the chosen reads -> ASCII rows
 //
-// Anything outside that grammar (wrapped sequences, blank lines between records, blanks inside a sequence) is
-// reported as APC_ERR_FORMAT by apc_ingest_fastx and is the host parser's job (csrc/host/host_util.cpp).
+// FASTA that is not one line per sequence (wrapped sequences, blank lines, headers without a sequence line) is first
+// re-laid as single-line records in a second buffer (measure_lines_kernel + prefix sum + unwrap_lines_kernel) and then
+// indexed like the rest.  Wrapped FASTQ and blanks inside a sequence line are reported as APC_ERR_FORMAT by
+// apc_ingest_fastx and are the host parser's job (csrc/host/host_util.cpp).
 #include <cub/device/device_scan.cuh>
 
 #include "apc_internal.h"
@@ -181,6 +182,39 @@ index_records_kernel(const LineTable t, const uint64_t n_records, uint64_t *__re
     if (lane == 0 && bad) atomicOr(flag, 1u);
 }
 
+// ---- wrapped FASTA -> single-line records --------------------------------------------------------------------------
+// A header line (first byte '>') opens a record; every other line adds its bytes, without trailing blanks, to the
+// record's sequence (blank lines add nothing — the host parser reads the same grammar).  The re-laid file is
+// ">\n" + sequence + "\n" per record, so the single-line kernels above index it; blanks INSIDE a line travel with it and
+// are caught there.  Line 0 is a header (apc_ingest_fastx checked the file's first byte).
+// bytes each line contributes: 2 for the first header (">\n"), 3 for the others ("\n>\n": the newline that closes the
+// previous record's sequence), its stripped length otherwise; one thread per line
+__global__ void measure_lines_kernel(const LineTable t, uint64_t *__restrict__ line_len) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > t.n_nl) {
+        if (i == t.n_nl + 1) line_len[i] = 0; // the slot that receives the total
+        return;
+    }
+    const uint64_t b = t.begin(i);
+    uint64_t e = t.end(i);
+    while (e > b && is_blank(t.file[e - 1])) e--;
+    line_len[i] = (e > b && t.file[b] == '>') ? (i == 0 ? 2 : 3) : e - b;
+}
+
+// one warp per line: the separator bytes of a header, or the line's bytes to their place in the re-laid file
+__global__ void __launch_bounds__(kIndexWarps * 32)
+unwrap_lines_kernel(const LineTable t, const uint64_t *__restrict__ line_off, uint8_t *__restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t i = (uint64_t)blockIdx.x * kIndexWarps + (threadIdx.x >> 5);
+    if (i > t.n_nl) return;
+    const uint64_t off = line_off[i], len = line_off[i + 1] - off, b = t.begin(i);
+    if (len && t.file[b] == '>') {
+        if (lane < len) out[off + lane] = (i == 0 ? ">\n" : "\n>\n")[lane];
+        return;
+    }
+    for (uint64_t j = lane; j < len; j += 32) out[off + j] = t.file[b + j];
+}
+
 // :447-461 — position i of the (shuffled) order is taken when its read has at least 2 * cut bases
 __global__ void pick_flag_kernel(const uint32_t *__restrict__ order, const uint64_t n, const uint32_t *__restrict__ rec_len,
                                  const uint64_t min_len, uint32_t *__restrict__ flags, uint32_t *__restrict__ flag) {
@@ -280,6 +314,20 @@ cudaError_t launch_index_records(const uint8_t *d_file, const uint64_t *d_nl, ui
     const unsigned grid = grid_for(n_records, kIndexWarps * 32);
     if (fastq) index_records_kernel<true><<<grid, kIndexWarps * 32, 0, s>>>(t, n_records, d_rec_start, d_rec_len, d_flag);
     else index_records_kernel<false><<<grid, kIndexWarps * 32, 0, s>>>(t, n_records, d_rec_start, d_rec_len, d_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_measure_lines(const uint8_t *d_file, const uint64_t *d_nl, uint64_t n_nl, uint64_t n_bytes,
+                                 uint64_t *d_line_len, cudaStream_t s) {
+    const LineTable t{d_file, d_nl, n_nl, n_bytes};
+    measure_lines_kernel<<<grid_for(n_nl + 2, 256), 256, 0, s>>>(t, d_line_len);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unwrap_lines(const uint8_t *d_file, const uint64_t *d_nl, uint64_t n_nl, uint64_t n_bytes,
+                                const uint64_t *d_line_off, uint8_t *d_out, cudaStream_t s) {
+    const LineTable t{d_file, d_nl, n_nl, n_bytes};
+    unwrap_lines_kernel<<<grid_for(n_nl + 1, kIndexWarps), kIndexWarps * 32, 0, s>>>(t, d_line_off, d_out);
     return cudaGetLastError();
 }
 

@@ -103,16 +103,18 @@ int apc_sample_info(const apc_ctx *ctx, uint64_t *n_reads, uint32_t *max_len,
 
 /* ---- ingest on the device: FASTA / FASTQ bytes -> sampled read ends -----------
  * Replaces readRecords (:819-825) and the walk and copies of sampleSequences
- * (:447-471) for inputs whose records keep their sequence on ONE line
- * (single-line FASTA: '>' header, sequence; 4-line FASTQ: '@' header, sequence,
- * '+' line, quality of the sequence's length; LF or CRLF; blank lines only at
- * the end of the file): the file's bytes are copied to HBM once, the records
- * are indexed there (newline index + one warp per record checking the grammar),
- * and every sample is gathered from the resident bytes straight into the
- * staging buffer of the layout kernels.  Any other input returns
- * APC_ERR_FORMAT and belongs to the host parser (apch_reads_load), which takes
- * wrapped records and stray blanks.  `file_bytes` is a HOST pointer (a read-only
- * mapping of the file will do); it is not needed after the call returns. */
+ * (:447-471): the file's bytes are copied to HBM once, the records are indexed
+ * there (newline index + a grammar check per record), and every sample is
+ * gathered from the resident bytes straight into the staging buffer of the
+ * layout kernels.  Taken: FASTA ('>' header lines; a record's other lines,
+ * trailing blanks dropped, are its sequence — wrapped sequences, blank lines
+ * and headers without a sequence line included: such files are re-laid as one
+ * line per sequence on the device first) and 4-line FASTQ ('@' header,
+ * sequence, '+' line, quality of the sequence's length); LF or CRLF.  Refused
+ * with APC_ERR_FORMAT, and left to the host parser (apch_reads_load): wrapped
+ * FASTQ, and blanks INSIDE a sequence line.  `file_bytes` is a HOST pointer (a
+ * read-only mapping of the file will do); it is not needed after the call
+ * returns. */
 int apc_ingest_fastx(apc_ctx *ctx, const uint8_t *file_bytes, uint64_t n_bytes,
                      uint64_t *n_records_out, int *is_fastq_out);
 /* seqs[first .. first+n) lengths (`length(sequence_set[id])`, :461) of the

@@ -132,13 +132,9 @@ def test_small_and_empty_inputs(built, counter):
 
 
 @pytest.mark.parametrize("data", [
-    b">a\nACGT\nACGT\n>b\nAC\n",                 # wrapped FASTA
-    b">a\nACGT\n\n>b\nAC\n",                     # blank line between records
-    b"\n>a\nACGT\n",                             # leading blank line
     b">a\nAC GT\n>b\nAC\n",                      # blank inside a sequence
     b">a\nAC\rGT\n>b\nAC\n",                     # CR inside a sequence
-    b">a\nACGT\n>b\n",                           # header without a sequence line
-    b">a\n>b\nACGT\n",                           # header directly after a header
+    b">a\nACGT\n  AC\n>b\nAC\n",                 # wrapped FASTA with blanks in front of a line
     b"@q\nACGT\n+\nIII\n",                       # quality shorter than the sequence
     b"@q\nACGT\n+\nIIII\n@r\nAC\n+\nIII\n",      # quality longer
     b"@q\nAC\nGT\n+\nII\nII\n",                  # wrapped FASTQ (line count still a multiple of 4 after this record?)
@@ -157,10 +153,60 @@ def test_inputs_outside_the_grammar_are_refused(built, counter, data):
     assert counter.ingest_fastx(b">a\nACGT\n") == (1, False)   # and the context is still usable
 
 
+def wrapped_fasta_bytes(reads, rng, eol=b"\n", width=None, blank_lines=False):
+    out = []
+    for i, s in enumerate(reads):
+        w = width or int(rng.integers(1, 90))
+        lines = [s[j:j + w] for j in range(0, len(s), w)]
+        if blank_lines and i % 5 == 0:
+            lines.insert(int(rng.integers(0, len(lines) + 1)), b"")          # a blank line inside the record
+        if blank_lines and i % 7 == 0:
+            lines.append(b" \t")                                            # a line of blanks in front of the next header
+        out.append(b">r%d wrapped" % i + eol + b"".join(l + eol for l in lines))
+    return b"".join(out)
+
+
+@pytest.mark.parametrize("eol,width,blank_lines,lead", [(b"\n", 60, False, b""), (b"\r\n", 70, False, b""),
+                                                        (b"\n", None, True, b"\n \n"), (b"\r\n", None, True, b"")])
+def test_wrapped_fasta_is_relaid_on_the_device(built, counter, tmp_path, eol, width, blank_lines, lead):
+    """FASTA with wrapped sequences, blank lines and headers without a sequence line: the device re-lays the records
+    on one line each and indexes that; records and samples equal the host parser's."""
+    from approx_counter_b200 import host
+    rng = np.random.default_rng(99 + len(eol) + (width or 0))
+    reads = random_reads(rng, 900, 0, 400)
+    reads[5] = b""
+    reads[-1] = b"" if blank_lines else reads[-1]          # the file ends with a header (and blank lines)
+    data = lead + wrapped_fasta_bytes(reads, rng, eol, width, blank_lines)
+    path = tmp_path / "w.fa"
+    path.write_bytes(data)
+    r, lens = host_view(path)
+    assert np.array_equal(lens, np.array([len(s) for s in reads], np.uint32))
+    assert counter.ingest_fastx(data) == (len(reads), False)
+    assert np.array_equal(counter.ingest_lengths(), lens)
+    cut = 50
+    order = host.shuffle_order(len(reads), 8)
+    for bot in (False, True):
+        want = r.sample(300, cut, bot, 8)
+        assert counter.sample_resident(300, cut, bot, order) == len(want) > 0
+        assert np.array_equal(counter.download_sample(), want)
+    # the same reads on one line each give the same resident state
+    single = fastx_bytes(reads, False)
+    assert counter.ingest_fastx(single) == (len(reads), False)
+    assert np.array_equal(counter.ingest_lengths(), lens)
+
+
+def test_fasta_edge_grammars_now_taken(built, counter):
+    for data, lens in ((b">a\nACGT\nACGT\n>b\nAC\n", [8, 2]), (b">a\nACGT\n\n>b\nAC\n", [4, 2]), (b"\n>a\nACGT\n", [4]),
+                       (b">a\nACGT\n>b\n", [4, 0]), (b">a\n>b\nACGT\n", [0, 4]), (b">\n>\n>\n", [0, 0, 0]),
+                       (b">a\r\nAC\r\nGT\r\n\r\n>b\r\n", [4, 0])):
+        assert counter.ingest_fastx(data) == (len(lens), False), data
+        assert counter.ingest_lengths().tolist() == lens, data
+
+
 @pytest.mark.parametrize("fastq,k,sl,lim,n", [(False, 16, 100, 200, 3000), (True, 20, 150, 300, 1500)])
 def test_binary_device_ingest_writes_the_same_files(built, tmp_path, fastq, k, sl, lim, n):
     """--ingest device against --ingest host: same four files for a sample that is a strict subset of the reads
-    (same --seed), and the host parser takes over for a wrapped FASTA."""
+    (same --seed), for a wrapped FASTA as well; the host parser takes over for blanks inside sequence lines."""
     from approx_counter_b200 import host
     path = tmp_path / ("reads.fq" if fastq else "reads.fa")
     host.synth_write(path, 777 + k, n, sl, fastq=fastq)
@@ -177,17 +223,18 @@ def test_binary_device_ingest_writes_the_same_files(built, tmp_path, fastq, k, s
     assert files["host"] == files["device"]
     if not fastq:
         r = host.Reads(path)
-        wrapped = tmp_path / "wrapped.fa"
-        with open(wrapped, "wb") as f:
-            for i in range(len(r)):
-                s = r.seq(i)
-                f.write(b">r%d\n" % i + b"\n".join(s[j:j + 70] for j in range(0, len(s), 70)) + b"\n")
-        p = subprocess.run([BIN, "-k", str(k), "-sn", str(n // 2), "-sl", str(sl), "-lim", str(lim), "--seed", "11",
-                            "--ingest", "device", "-v", "2", "-e", str(tmp_path / "e_w"), "-o", str(tmp_path / "o_w"),
-                            str(wrapped)], capture_output=True, text=True, timeout=300)
-        assert p.returncode == 0, p.stderr
-        assert "using the host parser" in p.stdout
-        assert [(tmp_path / f"{x}_w_0.{w}").read_bytes() for x in "eo" for w in ("start", "end")] == files["host"]
+        for name, sep, note in (("wrapped", b"\n", "indexed on the GPU"), ("blanks", b" \n ", "using the host parser")):
+            wrapped = tmp_path / f"{name}.fa"
+            with open(wrapped, "wb") as f:
+                for i in range(len(r)):
+                    s = r.seq(i)
+                    f.write(b">r%d\n" % i + sep.join(s[j:j + 70] for j in range(0, len(s), 70)) + b"\n")
+            p = subprocess.run([BIN, "-k", str(k), "-sn", str(n // 2), "-sl", str(sl), "-lim", str(lim), "--seed", "11",
+                                "--ingest", "device", "-v", "2", "-e", str(tmp_path / f"e_{name}"), "-o", str(tmp_path / f"o_{name}"),
+                                str(wrapped)], capture_output=True, text=True, timeout=300)
+            assert p.returncode == 0, p.stderr
+            assert note in p.stdout
+            assert [(tmp_path / f"{x}_{name}_0.{w}").read_bytes() for x in "eo" for w in ("start", "end")] == files["host"]
 
 
 def test_staged_copy_of_a_large_file(built, counter, tmp_path):
