@@ -72,6 +72,14 @@ def test_ingest_and_sampling_match_the_host_route(built, counter, tmp_path, fast
                 assert got_n == len(want) == min(want_n, eligible)
                 got = counter.download_sample()
                 assert got.shape == want.shape and np.array_equal(got, want)
+    # against the oracle's restatement of sampleSequences (:415-476) on the same reads and the same shuffled ids
+    all_codes, all_offs = orc.encode(reads)
+    order = host.shuffle_order(n, 5)
+    for bot in (False, True):
+        oc, oo = orc.sample_sequences(all_codes, all_offs, order, sn, cut, bot)
+        assert counter.sample_resident(sn, cut, bot, order) == len(oo) - 1
+        got_codes, got_offs = orc.encode_matrix(counter.download_sample())
+        assert np.array_equal(got_codes, oc) and np.array_equal(got_offs, oo)
     # the counts of the gathered sample == the counts of the same rows uploaded from the host
     k = 12
     want = r.sample(sn, cut, True, 5)
