@@ -10,7 +10,10 @@
 // C++14, header-only, no CUDA headers needed: it only calls the extern "C" functions of apc.h.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
+#include <numeric>
+#include <random>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -55,6 +58,33 @@ inline void upload(const sequence_set_type &sequences) {
     check(ctx, apc_upload_sample_ragged(ctx, reinterpret_cast<const uint8_t *>(flat.data()), offs.data(),
                                         sequences.size()),
           "apc_upload_sample_ragged");
+}
+
+// readRecords (:825) on the GPU: the bytes of the FASTA / FASTQ file (any host buffer or mapping) are copied to HBM and
+// the records indexed there.  Returns false when the file is one the device parser leaves to SeqAn (wrapped FASTQ,
+// blanks inside sequence lines): keep the readRecords route for it.  *n_seqs = length(seqs) (:831).
+inline bool readRecordsResident(const void *file_bytes, uint64_t n_bytes, uint64_t *n_seqs) {
+    apc_ctx *ctx = context();
+    int is_fastq = 0;
+    const int st = apc_ingest_fastx(ctx, static_cast<const uint8_t *>(file_bytes), n_bytes, n_seqs, &is_fastq);
+    if (st == APC_ERR_FORMAT) return false;
+    check(ctx, st, "apc_ingest_fastx");
+    return true;
+}
+
+// sampleSequences (:415-476) over the records readRecordsResident left on the GPU: the ids are shuffled here exactly
+// as in :423-429, the walk (:447-461) and the cuts (:463 / :466) happen on the device, and the sample stays there —
+// no upload() afterwards.  Returns the number of sampled reads (`Sampled n sequences`, :870).
+template <typename Rng>
+inline uint64_t sampleSequencesResident(uint64_t n_seqs, unsigned nb_sample, unsigned cut_size, bool botom, Rng &g) {
+    apc_ctx *ctx = context();
+    std::vector<uint32_t> vec(n_seqs);
+    std::iota(vec.begin(), vec.end(), 0u); // :424-426
+    std::shuffle(vec.begin(), vec.end(), g); // :429
+    uint64_t n_sampled = 0;
+    check(ctx, apc_sample_resident(ctx, vec.data(), vec.size(), nb_sample, cut_size, botom ? 1 : 0, &n_sampled),
+          "apc_sample_resident");
+    return n_sampled;
 }
 
 // count_kmers (:487) followed by get_most_frequent (:396, as called at :898): the `limit` most

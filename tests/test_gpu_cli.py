@@ -202,10 +202,13 @@ def test_reference_shim(built, tmp_path):
     subprocess.run(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
                     "-I", os.path.join(ROOT, "integration"), os.path.join(ROOT, "integration", "shim_demo.cpp"),
                     "-o", str(exe), "-L", libdir, "-lapc", f"-Wl,-rpath,{libdir}"], check=True)
-    p = subprocess.run([str(exe), str(path), str(k), str(sl), str(lim), "1.0", str(tmp_path / "shim")],
-                       capture_output=True, text=True, timeout=300)
-    assert p.returncode == 0, p.stderr
     r = host.Reads(path)
     want = oracle_files([r.seq(i) for i in range(len(r))], k, sl, lim, 1.0, tmp_path)
-    for which in ("start", "end"):
-        assert (tmp_path / f"shim_0.{which}").read_bytes() == want[which][1]
+    # the host's copy of the reads handed to upload(), then readRecords + sampleSequences on the GPU instead
+    for extra in ([], ["device"]):
+        p = subprocess.run([str(exe), str(path), str(k), str(sl), str(lim), "1.0", str(tmp_path / "shim")] + extra,
+                           capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr
+        for which in ("start", "end"):
+            assert (tmp_path / f"shim_0.{which}").read_bytes() == want[which][1]
+            os.unlink(tmp_path / f"shim_0.{which}")
