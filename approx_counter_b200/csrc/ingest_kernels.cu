@@ -28,16 +28,19 @@ constexpr int kIngestThreads = 256;                                     // 8 war
 constexpr int kIngestIters = (int)(kIngestTileBytes / (32 * 16));       // uint4 loads per lane and tile
 static_assert(kIngestIters * 32 * 16 == (int)kIngestTileBytes, "tile = 32 lanes x iterations x 16 bytes");
 
-// bit b of the result = byte b of the 16 is '\n'
+// bit 8 j + 7 of word i of the result = byte 4 i + j of the 16 is '\n'
+__device__ __forceinline__ uint4 newline_bits16(const uint4 v) {
+    return make_uint4(__vcmpeq4(v.x, 0x0A0A0A0Au) & 0x80808080u, __vcmpeq4(v.y, 0x0A0A0A0Au) & 0x80808080u,
+                      __vcmpeq4(v.z, 0x0A0A0A0Au) & 0x80808080u, __vcmpeq4(v.w, 0x0A0A0A0Au) & 0x80808080u);
+}
+__device__ __forceinline__ uint32_t popc4(const uint4 b) { return __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w); }
+// the same as one 16-bit mask: bit b = byte b of the 16 is '\n'
 __device__ __forceinline__ uint32_t newline_mask16(const uint4 v) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const uint4 b = newline_bits16(v);
+    const uint32_t w[4] = {b.x, b.y, b.z, b.w};
     uint32_t m = 0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t eq = __vcmpeq4(w[i], 0x0A0A0A0Au) & 0x08040201u; // byte j -> bit 9 j
-        eq = (eq | (eq >> 8) | (eq >> 16) | (eq >> 24)) & 0xFu;   // -> bit j
-        m |= eq << (4 * i);
-    }
+    for (int i = 0; i < 4; i++) m |= ((((w[i] >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * i); // bits 0, 8, 16, 24 -> 0..3
     return m;
 }
 
@@ -54,7 +57,7 @@ count_newlines_kernel(const uint4 *__restrict__ file, const uint64_t n_tiles, ui
         for (int it = 0; it < kIngestIters; it++) v[it] = __ldg(p + it * 32);
         uint32_t c = 0;
 #pragma unroll
-        for (int it = 0; it < kIngestIters; it++) c += __popc(newline_mask16(v[it]));
+        for (int it = 0; it < kIngestIters; it++) c += popc4(newline_bits16(v[it]));
         c = __reduce_add_sync(0xFFFFFFFFu, c);
         if (lane == 0) tile_nl[tile] = c;
     }
@@ -74,13 +77,25 @@ write_newlines_kernel(const uint4 *__restrict__ file, const uint64_t n_tiles, co
 #pragma unroll
         for (int it = 0; it < kIngestIters; it++) {
             uint32_t m = newline_mask16(v[it]);
-            if (!__any_sync(0xFFFFFFFFu, m != 0)) continue; // most 512-byte steps of a read file hold one newline or none
+            const uint32_t has = __ballot_sync(0xFFFFFFFFu, m != 0);
+            if (!has) continue; // 512-byte steps without a newline cost nothing more
             const uint32_t c = __popc(m);
-            uint32_t incl = c; // inclusive prefix over the warp
+            uint32_t incl = c, total; // inclusive prefix over the warp
+            if (__popc(has) <= 4) { // a few lanes hold newlines: their counts are handed round one by one
+                total = 0;
+                for (uint32_t rest = has; rest; rest &= rest - 1) {
+                    const uint32_t j = (uint32_t)__ffs((int)rest) - 1;
+                    const uint32_t cj = __shfl_sync(0xFFFFFFFFu, c, j);
+                    incl += j < lane ? cj : 0;
+                    total += cj;
+                }
+            } else {
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= (uint32_t)d) incl += o;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= (uint32_t)d) incl += o;
+                }
+                total = __shfl_sync(0xFFFFFFFFu, incl, 31);
             }
             uint64_t at = base + incl - c;
             const uint64_t byte0 = tile * kIngestTileBytes + ((uint64_t)it * 32 + lane) * 16;
@@ -88,7 +103,7 @@ write_newlines_kernel(const uint4 *__restrict__ file, const uint64_t n_tiles, co
                 nl[at++] = byte0 + (uint32_t)(__ffs((int)m) - 1);
                 m &= m - 1;
             }
-            base += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            base += total;
         }
     }
 }
