@@ -282,6 +282,37 @@ def ingest_leg(w, name, device):
             c.sample_resident(n, sl, bot, order)
             same = same and np.array_equal(c.download_sample(), rows[int(bot)])
         out["samples_identical"] = bool(same)
+        # the whole per-file pipeline through the C ABI, CUDA context and buffers warm (apc_reserve, as the binary does
+        # beside the creation of its context): file bytes (mapped) -> both ends' exact top-lim and approximate counts on
+        # the host (reference :819-928 without the export)
+        thr = host.adjust_threshold(PARAM_LC, 16, w["k"])
+        c.reserve(n, sl + 1, w["k"], w["lim"])
+        with open(path, "rb") as f:
+            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+            buf = np.frombuffer(mm, np.uint8)
+            t0 = time.perf_counter()
+            nrec, _ = c.ingest_fastx(buf)
+            t1 = time.perf_counter()
+            phases = {"ingest_ms": (t1 - t0) * 1e3, "shuffle_ms": 0.0, "sample_ms": 0.0, "exact_ms": 0.0, "approx_ms": 0.0}
+            for bot in (False, True):
+                ta = time.perf_counter()
+                order = host.shuffle_order(nrec, 7)
+                tb = time.perf_counter()
+                c.sample_resident(n, sl, bot, order)
+                tc = time.perf_counter()
+                km, _, _, _ = c.count_kmers_topn(w["k"], thr, w["lim"])
+                td = time.perf_counter()
+                c.errorCount(km, w["k"])
+                te = time.perf_counter()
+                phases["shuffle_ms"] += (tb - ta) * 1e3
+                phases["sample_ms"] += (tc - tb) * 1e3
+                phases["exact_ms"] += (td - tc) * 1e3
+                phases["approx_ms"] += (te - td) * 1e3
+            phases["total_ms"] = (time.perf_counter() - t0) * 1e3
+            del buf
+            mm.close()
+        out["pipeline_from_file"] = dict(phases, what="apc_ingest_fastx -> per end: apch_shuffle_order, apc_sample_resident, "
+                                         "apc_exact_topn, apc_approx_count (host in/out); wall clock, one pass, context warm")
         if not same:
             raise SystemExit("bench.py: PARITY FAILURE — device ingest and host ingest leave different samples")
     finally:
@@ -868,7 +899,8 @@ def run_b200(args, w):
         "wide_offset_value": wide["value"] if wide else None, "wide_offset": wide,
         "c2_weak_value": c2["value"] if c2 else None, "c2_weak": c2,
         "ingest_device_ms": ingest.get("device_ms") if ingest else None,
-        "ingest_host_ms": ingest.get("host_ms") if ingest else None, "ingest": ingest,
+        "ingest_host_ms": ingest.get("host_ms") if ingest else None,
+        "pipeline_from_file_ms": (ingest.get("pipeline_from_file") or {}).get("total_ms") if ingest else None, "ingest": ingest,
         "cpu_baseline": cpu,
     }
     emit(line)
