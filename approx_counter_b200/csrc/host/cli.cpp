@@ -420,7 +420,7 @@ int cli_main(int argc, const char **argv) {
             if (mr_v > 0) print(bottom ? "Sampling the ends of reads" : "Sampling the start of reads", 1);
             uint64_t n_sampled = 0;
             uint32_t row_len = 0;
-            std::vector<uint8_t> sample;
+            SampleBytes sample;
             int st = APC_OK;
             if (device_ingest) { // :867 on the device: the host only shuffles the ids (:423-429)
                 // when every read is wanted (sn >= #reads, :844-848) the walk takes ALL eligible reads whatever the

@@ -95,7 +95,7 @@ int apch_sample(const apch_reads *r, uint64_t nb_sample, uint64_t cut, int bot, 
     APCH_GUARD(-1,
     if (!r || !n_sampled) return -1;
     uint32_t row = 0;
-    const std::vector<uint8_t> s = apch::sample_sequences(*r, nb_sample, cut, bot != 0, seed, *n_sampled, row);
+    const apch::SampleBytes s = apch::sample_sequences(*r, nb_sample, cut, bot != 0, seed, *n_sampled, row);
     if (out && !s.empty()) std::memcpy(out, s.data(), s.size());
     return 0;
     )

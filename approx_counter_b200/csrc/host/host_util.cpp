@@ -568,8 +568,8 @@ std::vector<int> shuffle_order(uint64_t n, int64_t seed) { // :423-429
     return vec;
 }
 
-std::vector<uint8_t> sample_sequences(const Reads &reads, uint64_t nb_sample, uint64_t cut, bool bot,
-                                      int64_t seed, uint64_t &n_sampled, uint32_t &row_len) { // :415-476
+SampleBytes sample_sequences(const Reads &reads, uint64_t nb_sample, uint64_t cut, bool bot, int64_t seed,
+                             uint64_t &n_sampled, uint32_t &row_len) { // :415-476
     const uint64_t n = reads.size();
     const std::vector<int> vec = shuffle_order(n, seed);
     row_len = (uint32_t)(cut + (bot ? 1 : 0));
@@ -581,14 +581,24 @@ std::vector<uint8_t> sample_sequences(const Reads &reads, uint64_t nb_sample, ui
         if (cut > 0 && reads.length(id) >= cut * 2) chosen.push_back(id); // :461 (current_cut_size == cut_size here)
     }
     n_sampled = chosen.size();
-    std::vector<uint8_t> sample((size_t)n_sampled * row_len);
+    SampleBytes sample;
+    sample.n = (size_t)n_sampled * row_len;
+    sample.bytes.reset(new uint8_t[sample.n ? sample.n : 1]);
+    // suffix(seq, len-1-cut) :463 (cut+1 bases) / prefix(seq, cut) :466
+    auto source = [&](int64_t r) {
+        const uint64_t id = chosen[(size_t)r];
+        return reads.seq(id) + (bot ? reads.length(id) - 1 - cut : 0);
+    };
+    uint8_t *out = sample.data();
 #pragma omp parallel for schedule(static)
     for (int64_t r = 0; r < (int64_t)n_sampled; r++) {
-        const uint64_t id = chosen[(size_t)r];
-        const uint64_t len = reads.length(id);
-        const char *s = reads.seq(id);
-        // suffix(seq, len-1-cut) :463 (cut+1 bases) / prefix(seq, cut) :466
-        memcpy(&sample[(size_t)r * row_len], bot ? s + (len - 1 - cut) : s, row_len);
+        // the reads sit at random places of a file-sized buffer: every row is a TLB and cache miss, so the rows a
+        // few iterations ahead are requested now
+        if (r + 8 < (int64_t)n_sampled) {
+            const char *ahead = source(r + 8);
+            for (uint32_t b = 0; b < row_len; b += 64) __builtin_prefetch(ahead + b, 0, 0);
+        }
+        memcpy(out + (size_t)r * row_len, source(r), row_len);
     }
     return sample;
 }

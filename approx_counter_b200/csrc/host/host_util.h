@@ -61,8 +61,18 @@ bool read_fastx(const std::string &path, Reads &out, std::string &err);
 
 // :415-476.  Returns the ASCII sample matrix (n_sampled rows of cut [+1 if bot]).
 std::vector<int> shuffle_order(uint64_t n, int64_t seed); // :423-429
-std::vector<uint8_t> sample_sequences(const Reads &reads, uint64_t nb_sample, uint64_t cut, bool bot,
-                                      int64_t seed, uint64_t &n_sampled, uint32_t &row_len);
+// The sample's bytes without the zero fill a std::vector would do first (150 MB at C3: the pages are touched by the
+// threads that write them instead).
+struct SampleBytes {
+    std::unique_ptr<uint8_t[]> bytes;
+    size_t n = 0;
+    const uint8_t *data() const { return bytes.get(); }
+    uint8_t *data() { return bytes.get(); }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+};
+SampleBytes sample_sequences(const Reads &reads, uint64_t nb_sample, uint64_t cut, bool bot, int64_t seed,
+                             uint64_t &n_sampled, uint32_t &row_len);
 
 // synthetic ONT-like reads
 std::string synth_read(uint64_t seed, uint64_t index, uint32_t sl);
