@@ -94,9 +94,9 @@ int apch_sample(const apch_reads *r, uint64_t nb_sample, uint64_t cut, int bot, 
                 uint64_t *n_sampled) {
     APCH_GUARD(-1,
     if (!r || !n_sampled) return -1;
-    uint32_t row = 0;
-    const apch::SampleBytes s = apch::sample_sequences(*r, nb_sample, cut, bot != 0, seed, *n_sampled, row);
-    if (out && !s.empty()) std::memcpy(out, s.data(), s.size());
+    const std::vector<uint64_t> chosen = apch::sample_ids(*r, nb_sample, cut, seed);
+    *n_sampled = chosen.size();
+    if (out) apch::sample_gather(*r, chosen, cut, bot != 0, out); // straight into the caller's rows
     return 0;
     )
 }

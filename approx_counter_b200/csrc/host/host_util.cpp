@@ -568,38 +568,49 @@ std::vector<int> shuffle_order(uint64_t n, int64_t seed) { // :423-429
     return vec;
 }
 
-SampleBytes sample_sequences(const Reads &reads, uint64_t nb_sample, uint64_t cut, bool bot, int64_t seed,
-                             uint64_t &n_sampled, uint32_t &row_len) { // :415-476
+// :447-461 — the ids the walk over the shuffled order takes: the first nb_sample reads of at least 2 * cut bases
+std::vector<uint64_t> sample_ids(const Reads &reads, uint64_t nb_sample, uint64_t cut, int64_t seed) {
     const uint64_t n = reads.size();
     const std::vector<int> vec = shuffle_order(n, seed);
-    row_len = (uint32_t)(cut + (bot ? 1 : 0));
-    // the walk of :447-471 only needs the read lengths; the copies are done afterwards, in parallel
     std::vector<uint64_t> chosen;
     chosen.reserve((size_t)std::min<uint64_t>(nb_sample, n));
     for (uint64_t i = 0; chosen.size() < nb_sample && i < n; i++) { // :447
         const uint64_t id = (uint64_t)vec[i];
         if (cut > 0 && reads.length(id) >= cut * 2) chosen.push_back(id); // :461 (current_cut_size == cut_size here)
     }
-    n_sampled = chosen.size();
-    SampleBytes sample;
-    sample.n = (size_t)n_sampled * row_len;
-    sample.bytes.reset(new uint8_t[sample.n ? sample.n : 1]);
-    // suffix(seq, len-1-cut) :463 (cut+1 bases) / prefix(seq, cut) :466
+    return chosen;
+}
+
+// :463 / :466 — row r of `out` = suffix(seq, len-1-cut) (cut+1 bases) or prefix(seq, cut) of read chosen[r]; the copies
+// only need the walk's result, so they run in parallel
+void sample_gather(const Reads &reads, const std::vector<uint64_t> &chosen, uint64_t cut, bool bot, uint8_t *out) {
+    const uint32_t row_len = (uint32_t)(cut + (bot ? 1 : 0));
+    const int64_t n_sampled = (int64_t)chosen.size();
     auto source = [&](int64_t r) {
         const uint64_t id = chosen[(size_t)r];
         return reads.seq(id) + (bot ? reads.length(id) - 1 - cut : 0);
     };
-    uint8_t *out = sample.data();
 #pragma omp parallel for schedule(static)
-    for (int64_t r = 0; r < (int64_t)n_sampled; r++) {
+    for (int64_t r = 0; r < n_sampled; r++) {
         // the reads sit at random places of a file-sized buffer: every row is a TLB and cache miss, so the rows a
         // few iterations ahead are requested now
-        if (r + 8 < (int64_t)n_sampled) {
+        if (r + 8 < n_sampled) {
             const char *ahead = source(r + 8);
             for (uint32_t b = 0; b < row_len; b += 64) __builtin_prefetch(ahead + b, 0, 0);
         }
         memcpy(out + (size_t)r * row_len, source(r), row_len);
     }
+}
+
+SampleBytes sample_sequences(const Reads &reads, uint64_t nb_sample, uint64_t cut, bool bot, int64_t seed,
+                             uint64_t &n_sampled, uint32_t &row_len) { // :415-476
+    row_len = (uint32_t)(cut + (bot ? 1 : 0));
+    const std::vector<uint64_t> chosen = sample_ids(reads, nb_sample, cut, seed);
+    n_sampled = chosen.size();
+    SampleBytes sample;
+    sample.n = (size_t)n_sampled * row_len;
+    sample.bytes.reset(new uint8_t[sample.n ? sample.n : 1]);
+    sample_gather(reads, chosen, cut, bot, sample.data());
     return sample;
 }
 

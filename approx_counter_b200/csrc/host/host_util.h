@@ -71,6 +71,8 @@ struct SampleBytes {
     size_t size() const { return n; }
     bool empty() const { return n == 0; }
 };
+std::vector<uint64_t> sample_ids(const Reads &reads, uint64_t nb_sample, uint64_t cut, int64_t seed);               // :447-461
+void sample_gather(const Reads &reads, const std::vector<uint64_t> &chosen, uint64_t cut, bool bot, uint8_t *out); // :463 / :466
 SampleBytes sample_sequences(const Reads &reads, uint64_t nb_sample, uint64_t cut, bool bot, int64_t seed,
                              uint64_t &n_sampled, uint32_t &row_len);
 

@@ -122,7 +122,7 @@ class Reads:
     def sample(self, nb_sample, cut, bot, seed=-1):
         """sampleSequences (:415-476) -> uint8[n_sampled, cut (+1 if bot)] ASCII."""
         row = cut + (1 if bot else 0)
-        out = np.zeros((min(nb_sample, len(self)), row), np.uint8)
+        out = np.empty((min(nb_sample, len(self)), row), np.uint8)
         n = C.c_uint64()
         lib().apch_sample(self._h, int(nb_sample), int(cut), int(bool(bot)), int(seed),
                           out.ctypes.data, C.byref(n))
