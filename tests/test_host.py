@@ -292,3 +292,40 @@ def test_shuffle_order_is_the_samplers_order(built, tmp_path):
             got = r.sample(sn, cut, bot, seed)
             assert [row.tobytes() for row in got] == want
     assert len(host.shuffle_order(0, 1)) == 0
+
+
+def test_ingest_test_inputs_mean_what_the_gpu_tests_assume(built, tmp_path):
+    """The inputs tests/test_gpu_ingest.py feeds the device parser, through the HOST parser and the plain Python
+    parser of this file: the generators really produce the reads they are given, and the edge grammars have the record
+    lengths the GPU tests expect (so a GPU-side failure there is the device's, not the test's)."""
+    import importlib.util
+    from approx_counter_b200 import host
+    spec = importlib.util.spec_from_file_location("gpu_ingest_inputs", os.path.join(os.path.dirname(__file__), "test_gpu_ingest.py"))
+    gi = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gi)
+
+    def host_lens(data, name):
+        p = tmp_path / name
+        p.write_bytes(data)
+        r = host.Reads(p)
+        return [r.seq(i) for i in range(len(r))]
+
+    rng = np.random.default_rng(12)
+    reads = gi.random_reads(rng, 300, 0, 260)
+    for fastq in (False, True):
+        for eol, tail in ((b"\n", b"\n"), (b"\r\n", b"\r\n"), (b"\n", b""), (b"\n", b"\n\n \r\n\t\n")):
+            data = gi.fastx_bytes(reads, fastq, eol, tail)
+            assert host_lens(data, "a.fx") == reads
+            assert [s.encode() for s in _py_parse(data.decode())] == reads
+    for eol, width, blank_lines, lead in ((b"\n", 60, False, b""), (b"\r\n", 70, False, b""), (b"\n", None, True, b"\n \n"),
+                                          (b"\r\n", None, True, b"")):
+        rs = list(reads)
+        rs[5] = b""
+        if blank_lines:
+            rs[-1] = b""
+        data = lead + gi.wrapped_fasta_bytes(rs, rng, eol, width, blank_lines)
+        assert host_lens(data, "w.fa") == rs
+    for data, lens in ((b">a\nACGT\nACGT\n>b\nAC\n", [8, 2]), (b">a\nACGT\n\n>b\nAC\n", [4, 2]), (b"\n>a\nACGT\n", [4]),
+                       (b">a\nACGT\n>b\n", [4, 0]), (b">a\n>b\nACGT\n", [0, 4]), (b">\n>\n>\n", [0, 0, 0]),
+                       (b">a\r\nAC\r\nGT\r\n\r\n>b\r\n", [4, 0])):
+        assert [len(s) for s in host_lens(data, "e.fa")] == lens
