@@ -1,7 +1,7 @@
 // ingest_kernels.cu — K6: FASTA / FASTQ ingest and read sampling on the device.
 //
-// Replaces, for FASTA and 4-line FASTQ (what basecallers write), the reference's readRecords (:819-825) and the walk and copies of sampleSequences
-// (:447-471): the file's bytes are copied to HBM once, the records are indexed there, and every sample (start
+// Replaces, for FASTA and 4-line FASTQ (what basecallers write), the reference's readRecords (:819-825) and the walk
+// and copies of sampleSequences (:447-471): the file's bytes are copied to HBM once, the records are indexed there, and every sample (start
 // and end of a run, every run of -mr) is gathered from the resident bytes straight into the staging buffer the
 // layout kernels read — no host parse, no host-side copies of the read ends, no second upload.
 //
@@ -9,7 +9,7 @@
 //   [prefix sum over the tiles: cub::DeviceScan, tiles = bytes / 4096 elements]
 //   write_newlines_kernel   second pass: the byte offset of every newline, ascending    (reads 1 B / B, L2-warm for
 //                                                                                         files below ~100 MB)
-//   index_records_kernel    one warp per record: grammar check (header / '+' markers, quality length, no blanks
+//   index_records_kernel    one warp per 32 records: grammar check (header / '+' markers, quality length, no blanks
 //                           inside the sequence) and the record's (sequence offset, length)
 //   pick_*_kernel + prefix  the first nb_sample ids of the caller's shuffled order with length >= 2*cut (:447-461)
 //   gather_ends_kernel      prefix(cut) (:466) or the last cut+1 bases (:463) of the chosen reads -> ASCII rows
