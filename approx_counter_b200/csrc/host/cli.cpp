@@ -334,9 +334,9 @@ int cli_main(int argc, const char **argv) {
         // records are indexed and every sample is gathered (apc_ingest_fastx / apc_sample_resident).
         MappedFile file;
         if (!file.open(input_file)) {
-            std::cerr << error_pref << "could not open " << input_file << std::endl;
-            return 1;
-        }
+            // a pipe, or a file that is not there: the host parser reads the former and reports the latter
+            if (v > 1) print("Input cannot be mapped; using the host parser", tab_level);
+        } else {
         if (v > 1) print("File mapped; waiting for the CUDA context", tab_level);
         creator.join();
         if (create_status != APC_OK) return gpu_fail("cannot open CUDA device", nullptr, create_status);
@@ -357,6 +357,7 @@ int cli_main(int argc, const char **argv) {
             if (v > 1) print(std::string("Device parser: ") + apc_last_error(gpus[0].ctx) + "; using the host parser", tab_level);
         } else {
             return gpu_fail("copying the input to the GPU", gpus[0].ctx, st);
+        }
         }
     }
     if (!device_ingest) {

@@ -212,3 +212,27 @@ def test_reference_shim(built, tmp_path):
         for which in ("start", "end"):
             assert (tmp_path / f"shim_0.{which}").read_bytes() == want[which][1]
             os.unlink(tmp_path / f"shim_0.{which}")
+
+
+def test_binary_reads_a_pipe(built, tmp_path):
+    """The default route maps the input; a pipe cannot be mapped and goes to the host parser (which reads it whole):
+    same files as from the file itself."""
+    from approx_counter_b200 import host
+    path = tmp_path / "reads.fa"
+    host.synth_write(path, 808, 1200, 60)
+    outs = {}
+    for name, source in (("file", str(path)), ("pipe", "/dev/stdin")):
+        cmd = [BIN, "-k", "12", "-sn", "1200", "-sl", "60", "-lim", "80", "-v", "2", "-o", str(tmp_path / name), source]
+        if name == "pipe":
+            cat = subprocess.Popen(["cat", str(path)], stdout=subprocess.PIPE)
+            p = subprocess.run(cmd, stdin=cat.stdout, capture_output=True, text=True, timeout=300)
+            cat.wait()
+        else:
+            p = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr
+        assert ("using the host parser" in p.stdout) == (name == "pipe")
+        outs[name] = [(tmp_path / f"{name}_0.{w}").read_bytes() for w in ("start", "end")]
+    assert outs["file"] == outs["pipe"] and len(outs["file"][0]) > 0
+    p = subprocess.run([BIN, "-k", "12", "-o", str(tmp_path / "none"), str(tmp_path / "missing.fa")], capture_output=True,
+                       text=True, timeout=300)
+    assert p.returncode == 1 and "could not open" in p.stderr
